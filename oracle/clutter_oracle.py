@@ -1,0 +1,149 @@
+"""Oracle for the clutter cancellers (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+
+``ls_filter_oracle``   follows ``LS_Filter``, reference
+                       ``/root/reference/passiveRadar/clutter_removal.py:6-56``:
+                       :31 lags = -peek .. filterLen-1, :34-36 A[:,k] = roll(ref, lags[k]),
+                       :39 Gram A^H A, :42-45 Tikhonov solve, :51 srv - A @ taps.
+                       All arithmetic stays complex64 (OpenBLAS cgemm/cgemv, LAPACK cgesv)
+                       exactly as in the reference.
+``nlms_filter_oracle`` follows ``NLMS_filter`` (``:189-249``, update rule ``:211-215``).
+``block_nlms_oracle``  DEFINES ``block_NLMS``.  The reference has no such function
+                       (``grep -rn NLMS`` finds only ``NLMS_filter`` and ``GAL_JPE``), so for
+                       ``blockLen > 1`` parity is unpinned; ``blockLen == 1`` is pinned to
+                       ``NLMS_filter`` by tests/test_oracle_golden.py.
+``*_truth``            float64 evaluations of the same formulas.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _same_length(ref, srv):
+    if ref.shape != srv.shape:
+        raise ValueError('Input vectors must have the same length')
+
+
+# --------------------------------------------------------------------------- LS
+
+def ls_filter_oracle(refChannel, srvChannel, filterLen, reg=1.0, peek=10, return_filter=False):
+    refChannel = np.asarray(refChannel)
+    srvChannel = np.asarray(srvChannel)
+    _same_length(refChannel, srvChannel)
+    n = refChannel.shape[0]
+    ntaps = filterLen + peek
+    # column k of the data matrix is the reference delayed (circularly) by k - peek samples
+    delays = np.arange(ntaps) - peek
+    data = np.zeros((n, ntaps), dtype=np.complex64)
+    for col, dly in enumerate(delays):
+        data[:, col] = np.roll(refChannel, dly)
+    data_h = data.conj().T
+    gram = data_h @ data
+    ridge = np.eye(ntaps, dtype=np.complex64) * reg
+    taps = np.linalg.solve(gram + ridge, data_h @ srvChannel)
+    cleaned = srvChannel - data @ taps
+    return (cleaned, taps) if return_filter else cleaned
+
+
+def ls_filter_truth(ref, srv, filter_len, reg=1.0, peek=10):
+    """float64 LS_Filter via the circulant identities of SURVEY.md section 3.3.
+
+    Gram[a,b] = c[(a-b) mod N],  c[m] = sum_i conj(ref[i]) ref[(i+m) mod N]
+    rhs[a]    = x[(a-peek) mod N], x[m] = sum_i conj(ref[i]) srv[(i+m) mod N]
+    Returns (cleaned, taps) in complex128.
+    """
+    import scipy.linalg as sla
+    ref = np.asarray(ref, dtype=np.complex128)
+    srv = np.asarray(srv, dtype=np.complex128)
+    _same_length(ref, srv)
+    n = ref.shape[0]
+    m = filter_len + peek
+    fr = np.fft.fft(ref)
+    c = np.fft.ifft(np.conj(fr) * fr)
+    x = np.fft.ifft(np.conj(fr) * np.fft.fft(srv))
+    col = c[np.arange(m) % n].copy()
+    row = np.conj(col)
+    gram = sla.toeplitz(col, row)
+    rhs = x[(np.arange(m) - peek) % n]
+    taps = np.linalg.solve(gram + reg * np.eye(m), rhs)
+    h = np.zeros(n, dtype=np.complex128)
+    h[(np.arange(m) - peek) % n] += taps     # clutter[i] = sum_k taps[k] ref[i - (k - peek)]
+    clutter = np.fft.ifft(fr * np.fft.fft(h))
+    return srv - clutter, taps
+
+
+# ------------------------------------------------------------------------- NLMS
+
+def nlms_filter_oracle(refChannel, srvChannel, filterLen, mu, peek=10, initialTaps=None,
+                       returnFilter=False):
+    """Sample-serial NLMS in complex64, one Python iteration per sample (slow: ~8 us/sample)."""
+    return block_nlms_oracle(refChannel, srvChannel, filterLen, mu, peek=peek, blockLen=1,
+                             initialTaps=initialTaps, returnFilter=returnFilter)
+
+
+def block_nlms_oracle(refChannel, srvChannel, filterLen, mu, peek=10, blockLen=1,
+                      initialTaps=None, returnFilter=False):
+    """Block NLMS.  Definition (ours; DESIGN.md "block_NLMS"):
+
+    With M = filterLen + peek taps w and the regressor u_n[j] = ref[n + peek - j], j = 0..M-1,
+    for desired-sample index n = filterLen .. N - peek - 1, processed in consecutive blocks of
+    ``blockLen`` samples:
+
+        e_n = srv[n] - w^H u_n                      (w frozen inside a block)
+        w  <- w + mu * sum_{n in block} u_n conj(e_n) / (u_n^H u_n)     (at block end)
+
+    The final block may be shorter.  out[n] = e_n, out[:filterLen] = out[N-peek:] = 0.
+    ``blockLen == 1`` is exactly the recurrence of the reference's ``NLMS_filter``.
+    """
+    refChannel = np.asarray(refChannel)
+    srvChannel = np.asarray(srvChannel)
+    if initialTaps is None:
+        w = np.zeros((filterLen + peek,), dtype=np.complex64)
+    else:
+        w = initialTaps
+        filterLen = initialTaps.shape[0] - peek
+    ntaps = filterLen + peek
+    n = srvChannel.shape[0]
+    out = np.zeros(srvChannel.shape, dtype=np.complex64)
+    nsteps = n - filterLen - peek
+    k = 0
+    while k < nsteps:
+        kend = min(nsteps, k + blockLen)
+        grad = None
+        for kk in range(k, kend):
+            # u[j] = ref[ntaps + kk - j]
+            u = refChannel[kk + 1: kk + ntaps + 1][::-1]
+            e = srvChannel[kk + filterLen] - w.conj() @ u
+            step = mu * u * e.conj() / (u.conj() @ u)
+            grad = step if grad is None else grad + step
+            out[filterLen + kk] = e
+        w = w + grad
+        k = kend
+    return (out, w) if returnFilter else out
+
+
+def block_nlms_truth(ref, srv, filter_len, mu, peek=10, block_len=1, initial_taps=None):
+    """float64 version of ``block_nlms_oracle`` (vectorised per block). Returns (out, w)."""
+    ref = np.asarray(ref, dtype=np.complex128)
+    srv = np.asarray(srv, dtype=np.complex128)
+    if initial_taps is None:
+        w = np.zeros(filter_len + peek, dtype=np.complex128)
+    else:
+        w = np.asarray(initial_taps, dtype=np.complex128).copy()
+        filter_len = w.shape[0] - peek
+    ntaps = filter_len + peek
+    n = srv.shape[0]
+    out = np.zeros(n, dtype=np.complex128)
+    nsteps = n - filter_len - peek
+    from numpy.lib.stride_tricks import sliding_window_view
+    if nsteps <= 0:
+        return out, w
+    win = sliding_window_view(ref, ntaps)       # win[s, t] = ref[s + t]
+    for k in range(0, nsteps, block_len):
+        kend = min(nsteps, k + block_len)
+        # u_kk[j] = ref[kk + ntaps - j] = win[kk + 1, ntaps - 1 - j]
+        U = win[k + 1: kend + 1, ::-1]          # (B, ntaps)
+        e = srv[k + filter_len: kend + filter_len] - U @ np.conj(w)
+        nrm = np.einsum('bj,bj->b', np.conj(U), U).real
+        w = w + mu * (U * (np.conj(e) / nrm)[:, None]).sum(axis=0)
+        out[k + filter_len: kend + filter_len] = e
+    return out, w

@@ -1,0 +1,60 @@
+"""Helpers shared by the parity tests: load goldens, rebuild their seeded inputs."""
+import os
+
+import numpy as np
+import scipy.signal as signal
+
+from passiveradar_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    with np.load(path, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def have(name):
+    return os.path.exists(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def inputs(g):
+    """(ref, srv) of a golden: stored arrays when present, else regenerated from the seed
+    and checked against the stored fingerprint (guards against RNG-stream drift)."""
+    if "ref" in g:
+        return g["ref"], g["srv"]
+    ref, srv = synth.make_frame(int(g["n"]), str(g["profile"]), int(g["frame"]))
+    np.testing.assert_array_equal(synth.frame_digest(ref, srv), g["digest"])
+    return ref, srv
+
+
+def xambg_args(g):
+    """Positional args (after ref, srv) the golden was generated with."""
+    n = int(g["n"])
+    input_len = None if int(g["input_len"]) < 0 else int(g["input_len"])
+    nn = n if input_len is None else input_len
+    w = str(g["window"])
+    if w == "kaiser":
+        window = signal.get_window(("kaiser", 5.0), nn)
+    elif w == "tuple":
+        window = ("kaiser", 5.0)
+    else:
+        window = None
+    return int(g["R"]), int(g["F"]), input_len, window, bool(g["short_filt"])
+
+
+def rel_inf(a, b, den=None):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    d = np.abs(b).max() if den is None else den
+    return float(np.abs(a - b).max() / d)
+
+
+XAMBG_SMALL = ["xambg_small_kaiser", "xambg_small_nowin", "xambg_pad_tuple", "xambg_longfilt",
+               "xambg_decim1", "xambg_decim2", "xambg_odd_d251", "xambg_even_d250",
+               "xambg_tail_ignored", "xambg_r_ge_n", "xambg_nonpow2_F"]
+XAMBG_C1 = ["xambg_c1_p1", "xambg_c1_p0"]
+LS_SMALL = ["ls_small", "ls_small_peek0", "ls_small_reg0", "ls_mid"]
+LS_C1 = ["ls_c1_p1", "ls_c1_p0"]
+NLMS_ALL = ["nlms_small", "nlms_small_init", "nlms_peek0", "nlms_mid"]
