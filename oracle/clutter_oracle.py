@@ -147,3 +147,31 @@ def block_nlms_truth(ref, srv, filter_len, mu, peek=10, block_len=1, initial_tap
         w = w + mu * (U * (np.conj(e) / nrm)[:, None]).sum(axis=0)
         out[k + filter_len: kend + filter_len] = e
     return out, w
+
+
+# ------------------------------------------------------------------ plain-C NLMS (fast oracle)
+
+def block_nlms_oracle_c(ref, srv, filter_len, mu, peek=10, block_len=1, initial_taps=None):
+    """Same recurrence as ``block_nlms_oracle`` in plain C (oracle/nlms_oracle.c), complex float
+    arithmetic; ~100x faster than the Python loop.  Returns (out, taps)."""
+    import ctypes as C
+    from . import build as _b
+    lib = C.CDLL(_b.build())
+    fn = lib.nlms_oracle_c64
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_float, C.c_int,
+                   C.c_void_p, C.c_void_p, C.c_void_p]
+    ref = np.ascontiguousarray(ref, dtype=np.complex64)
+    srv = np.ascontiguousarray(srv, dtype=np.complex64)
+    init = None
+    if initial_taps is not None:
+        init = np.ascontiguousarray(initial_taps, dtype=np.complex64)
+        filter_len = init.shape[0] - peek
+    m = filter_len + peek
+    out = np.empty(srv.shape[0], dtype=np.complex64)
+    taps = np.empty(m, dtype=np.complex64)
+    st = fn(ref.ctypes.data, srv.ctypes.data, srv.shape[0], filter_len, peek, mu, block_len,
+            None if init is None else init.ctypes.data, out.ctypes.data, taps.ctypes.data)
+    if st != 0:
+        raise MemoryError("nlms_oracle_c64 failed")
+    return out, taps

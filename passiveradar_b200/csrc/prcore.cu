@@ -1,0 +1,772 @@
+// prcore.cu -- host side of libprcore.so: C ABI (include/prcore.h), workspaces, launches.
+//
+// Build (see passiveradar_b200/build.py):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+//        -Xcompiler -fPIC -shared -Iinclude -o passiveradar_b200/libprcore.so prcore.cu
+//
+// Threading model: one workspace ("Ctx") per (device, caller stream), or per
+// (device, calling thread) when the caller passes stream == NULL.  A Ctx owns grow-only
+// device buffers; all work of one call is enqueued on the Ctx's stream, so buffer reuse
+// is ordered by the stream.  Nothing here falls back to the CPU.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "prcore.h"
+#include "kernels.cuh"
+#include "nlms.cuh"
+
+namespace {
+
+using namespace prc;
+
+// slide_mac tile shapes: 10 x 10 complex MACs per step, lane stride
+// 10 complex = 80 B (odd multiple of 16 B => conflict-free 128-bit shared loads).
+constexpr int LC_TI = 10, LC_TD = 10;     // lagcorr: samples x lags per step
+constexpr int FIR_TK = 10, FIR_TO = 10;   // fir: taps x outputs per step
+constexpr int FIR_THREADS = 128;
+constexpr size_t SMEM_LIMIT = 200 * 1024;
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+// optional per-kernel timing (prc_profile_*): CUDA events on the launching stream around each launch
+enum KernelId { K_LAGCORR_LS = 0, K_LEVINSON, K_FIR, K_LAGCORR_CAF, K_DOPPLER, K_NLMS, K_MISC, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"lagcorr_ls", "levinson", "fir_apply", "lagcorr_caf",
+                                           "doppler_fft", "nlms", "misc"};
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+double g_prof_ms[K_COUNT] = {0};
+uint64_t g_prof_n[K_COUNT] = {0};
+struct ProfRec { int id; cudaEvent_t a, b; };
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(PRC_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                             \
+    } while (0)
+
+#define TRY(call)               \
+    do {                        \
+        int r_ = (call);        \
+        if (r_ != PRC_OK) return r_; \
+    } while (0)
+
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return PRC_OK;
+        if (p) {
+            cudaError_t e = cudaFree(p);   // implicit device sync: nothing in flight still uses it
+            p = nullptr;
+            cap = 0;
+            if (e != cudaSuccess) return fail(PRC_E_CUDA, "cudaFree: %s", cudaGetErrorString(e));
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(PRC_E_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return PRC_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int nsm = 148;
+    std::mutex mu;
+    DBuf ref, srv, out, clean, partial, win32, win64, dtaps32, dtaps64, lstaps, tw, pbuf, status,
+        nl_init, nl_taps;
+    int tw_F = 0;
+    std::vector<ProfRec> recs;
+    void release() {
+        cudaSetDevice(device);
+        for (DBuf* b : {&ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
+                        &tw, &pbuf, &status, &nl_init, &nl_taps})
+            b->release();
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+std::mutex g_mu;
+std::map<std::pair<int, void*>, Ctx*> g_stream_ctx;   // (device, caller stream)
+std::vector<Ctx*> g_all_ctx;
+std::atomic<bool> g_attrs_set[64];
+std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
+int g_tune_nchunk = -1, g_tune_g = -1;
+std::once_flag g_env_once;
+
+struct TlsCtx {
+    Ctx* ctx[64] = {nullptr};
+    uint64_t epoch = 0;
+};
+thread_local TlsCtx g_tls;
+
+void read_env() {
+    if (const char* e = getenv("PRC_TUNE_NCHUNK")) g_tune_nchunk = atoi(e);
+    if (const char* e = getenv("PRC_TUNE_G")) g_tune_g = atoi(e);
+}
+
+int set_kernel_attrs(int device) {
+    if (g_attrs_set[device].load()) return PRC_OK;
+    const int lim = (int)SMEM_LIMIT;
+    CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(levinson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(doppler_fft_pow2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(doppler_fft_pow2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(doppler_fft_pow2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    g_attrs_set[device].store(true);
+    return PRC_OK;
+}
+
+int get_ctx(int device, void* stream, Ctx** out) {
+    std::call_once(g_env_once, read_env);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PRC_E_CUDA, "no CUDA device available (%s); libprcore has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev || device >= 64) return fail(PRC_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    TRY(set_kernel_attrs(device));
+    if (stream == nullptr) {
+        if (g_tls.epoch != g_epoch.load()) {
+            for (auto& c : g_tls.ctx) c = nullptr;
+            g_tls.epoch = g_epoch.load();
+        }
+        Ctx*& c = g_tls.ctx[device];
+        if (!c) {
+            Ctx* n = new Ctx();
+            n->device = device;
+            n->own_stream = true;
+            cudaError_t se = cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking);
+            if (se != cudaSuccess) {
+                delete n;
+                return fail(PRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se));
+            }
+            cudaDeviceGetAttribute(&n->nsm, cudaDevAttrMultiProcessorCount, device);
+            std::lock_guard<std::mutex> lk(g_mu);
+            g_all_ctx.push_back(n);
+            c = n;
+        }
+        *out = c;
+        return PRC_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(device, stream);
+    auto it = g_stream_ctx.find(key);
+    if (it == g_stream_ctx.end()) {
+        Ctx* n = new Ctx();
+        n->device = device;
+        n->stream = static_cast<cudaStream_t>(stream);
+        n->own_stream = false;
+        cudaDeviceGetAttribute(&n->nsm, cudaDevAttrMultiProcessorCount, device);
+        g_all_ctx.push_back(n);
+        it = g_stream_ctx.emplace(key, n).first;
+    }
+    *out = it->second;
+    return PRC_OK;
+}
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PRC_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return PRC_OK;
+}
+
+struct ProfScope {          // brackets one launch with events when profiling is enabled
+    Ctx* c;
+    int id;
+    cudaEvent_t a = nullptr;
+    ProfScope(Ctx* c_, int id_) : c(c_), id(id_) {
+        if (g_prof_on.load(std::memory_order_relaxed)) {
+            cudaEventCreate(&a);
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~ProfScope() {
+        if (a) {
+            cudaEvent_t b;
+            cudaEventCreate(&b);
+            cudaEventRecord(b, c->stream);
+            c->recs.push_back({id, a, b});
+        }
+    }
+};
+
+// --------------------------------------------------------------------------- geometry
+struct Geo {
+    int H, G, steps, nchunk, chunk_len, threads;
+    size_t smem;
+    int HT;
+};
+
+int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int choose_geo(int blk_len, long long outer, int nlag, int nsm, Geo* g) {
+    const int TI = LC_TI, TD = LC_TD;
+    g->H = ceil_div(nlag, TD);
+    g->HT = g->H * TD;
+    if (g->H > 512) return fail(PRC_E_INVALID, "%d lags exceed the supported maximum of %d", nlag, 512 * TD);
+    int gmax = std::max(1, std::min(32, 256 / g->H));
+    if (g_tune_g > 0) gmax = std::max(1, std::min(g_tune_g, 512 / g->H));
+    long long target = (long long)nsm * 8;
+    long long nchunk = std::max<long long>(1, (target + outer - 1) / outer);
+    const int min_chunk = TI * gmax * 2;
+    nchunk = std::min<long long>(nchunk, std::max(1, blk_len / min_chunk));
+    if (g_tune_nchunk > 0) nchunk = std::min<long long>(g_tune_nchunk, blk_len);
+    for (;;) {
+        g->chunk_len = ceil_div(blk_len, nchunk);
+        g->nchunk = ceil_div(blk_len, g->chunk_len);
+        g->G = std::max(1, std::min(gmax, ceil_div(g->chunk_len, TI * 4)));
+        g->steps = ceil_div(ceil_div(g->chunk_len, g->G), TI);
+        const size_t Lpad = (size_t)g->G * g->steps * TI;
+        g->smem = std::max(2 * Lpad + g->HT, (size_t)g->G * g->HT) * sizeof(float2);
+        if (g->smem <= 100 * 1024 || g->chunk_len <= TI) break;
+        nchunk = nchunk * 2;
+    }
+    if (g->smem > SMEM_LIMIT) return fail(PRC_E_INVALID, "lag-correlation tile needs %zu B of shared memory", g->smem);
+    g->threads = ((g->H * g->G + 31) / 32) * 32;
+    return PRC_OK;
+}
+
+// --------------------------------------------------------------------------- device pipelines
+// All pointers are device pointers; everything is enqueued on c->stream.
+
+int decimator_offset(long long ntaps, long long D) {   // resample_poly alignment, up = 1
+    const long long half = (ntaps - 1) / 2;
+    const long long pre_pad = D - half % D;
+    const long long pre_remove = (half + pre_pad) / D;
+    return (int)(pre_remove * D - pre_pad);
+}
+
+int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int R, int F,
+                 const float* win32, const float* dtaps32, long long ndtaps, float2* out) {
+    if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
+    if (F < 1 || R < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", F, R);
+    const long long D = n / F;
+    if (D < 1) return fail(PRC_E_INVALID, "decimation factor int(n/freq_bins) is 0 (n=%lld, freq_bins=%d)", n, F);
+    long long ntaps;
+    int c0;
+    const float* taps = nullptr;
+    if (D == 1) {            // resample_poly(x, 1, 1) returns x (scipy _signaltools.py:4028)
+        ntaps = 1;
+        c0 = 0;
+    } else if (dtaps32 == nullptr) {
+        ntaps = D + 1;
+        c0 = decimator_offset(ntaps, D);
+    } else {
+        ntaps = ndtaps;
+        c0 = decimator_offset(ntaps, D);
+        taps = dtaps32;
+    }
+    if (ntaps > (1ll << 30)) return fail(PRC_E_INVALID, "decimator too long");
+    Geo g;
+    TRY(choose_geo((int)ntaps, F, R + 1, c->nsm, &g));
+    TRY(c->partial.ensure((size_t)F * g.nchunk * g.HT * sizeof(float2)));
+
+    LagCorrParams p{};
+    p.x = ref;
+    p.s[0] = srv; p.s[1] = srv;
+    p.dmin[0] = 0; p.dmin[1] = 0;
+    p.win = win32;
+    p.taps = taps;
+    p.n = (int)n;
+    p.blk_first_lo = (long long)c0 - (ntaps - 1);
+    p.blk_stride = D;
+    p.blk_len = (int)ntaps;
+    p.nblk = F;
+    p.nchunk = g.nchunk;
+    p.chunk_len = g.chunk_len;
+    p.H = g.H; p.G = g.G; p.steps = g.steps;
+    p.partial = c->partial.as<float2>();
+    {
+        ProfScope ps(c, K_LAGCORR_CAF);
+        lagcorr_kernel<LC_TI, LC_TD><<<dim3((unsigned)((long long)F * g.nchunk), 1), g.threads, g.smem, c->stream>>>(p);
+    }
+    TRY(check_launch("lagcorr_kernel(caf)"));
+
+    // Doppler stage
+    if (c->tw_F != F) {
+        TRY(c->tw.ensure((size_t)F * sizeof(float2)));
+        twiddle_kernel<<<ceil_div(F, 256), 256, 0, c->stream>>>(c->tw.as<float2>(), F);
+        TRY(check_launch("twiddle_kernel"));
+        c->tw_F = F;
+    }
+    DopplerParams d{};
+    d.partial = c->partial.as<float2>();
+    d.tw = c->tw.as<float2>();
+    d.out = out;
+    d.F = F; d.R = R; d.nchunk = g.nchunk; d.HT = g.HT;
+    int logF = 0;
+    while ((1 << logF) < F) ++logF;
+    d.logF = logF;
+    const bool pow2 = (1 << logF) == F && F >= 2;
+    ProfScope ps_doppler(c, K_DOPPLER);
+    if (pow2 && F <= 8192) {
+        if (F <= 1024) {
+            const size_t sm = (size_t)2 * F * 8 * sizeof(float2);
+            doppler_fft_pow2_kernel<8><<<ceil_div(R + 1, 8), 256, sm, c->stream>>>(d);
+        } else if (F <= 4096) {
+            const size_t sm = (size_t)2 * F * 2 * sizeof(float2);
+            doppler_fft_pow2_kernel<2><<<ceil_div(R + 1, 2), 256, sm, c->stream>>>(d);
+        } else {
+            const size_t sm = (size_t)2 * F * sizeof(float2);
+            doppler_fft_pow2_kernel<1><<<R + 1, 256, sm, c->stream>>>(d);
+        }
+        TRY(check_launch("doppler_fft_pow2_kernel"));
+    } else {
+        TRY(c->pbuf.ensure((size_t)F * (R + 1) * sizeof(float2)));
+        chunk_sum_kernel<<<ceil_div((long long)F * (R + 1), 256), 256, 0, c->stream>>>(
+            c->partial.as<float2>(), c->pbuf.as<float2>(), F, R, g.nchunk, g.HT);
+        TRY(check_launch("chunk_sum_kernel"));
+        doppler_dft_kernel<<<dim3(ceil_div(R + 1, 128), F), 128, 0, c->stream>>>(
+            c->pbuf.as<float2>(), c->tw.as<float2>(), out, F, R);
+        TRY(check_launch("doppler_dft_kernel"));
+    }
+    return PRC_OK;
+}
+
+int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek,
+              double reg, float2* out, float2* taps_out) {
+    if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
+    if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
+        return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
+    const int M = filter_len + peek;
+    if ((size_t)5 * M * sizeof(double2) > SMEM_LIMIT) return fail(PRC_E_INVALID, "%d taps exceed the solver's shared memory", M);
+    Geo g;
+    TRY(choose_geo((int)n, 2, M, c->nsm, &g));
+    TRY(c->partial.ensure((size_t)2 * g.nchunk * g.HT * sizeof(float2)));
+    TRY(c->lstaps.ensure((size_t)M * sizeof(float2)));
+    TRY(c->status.ensure(sizeof(int)));
+
+    LagCorrParams p{};
+    p.x = ref;
+    p.s[0] = ref; p.s[1] = srv;
+    p.dmin[0] = 0; p.dmin[1] = -peek;
+    p.win = nullptr; p.taps = nullptr;
+    p.n = (int)n;
+    p.blk_first_lo = 0;
+    p.blk_stride = 0;
+    p.blk_len = (int)n;
+    p.nblk = 1;
+    p.nchunk = g.nchunk;
+    p.chunk_len = g.chunk_len;
+    p.H = g.H; p.G = g.G; p.steps = g.steps;
+    p.partial = c->partial.as<float2>();
+    {
+        ProfScope ps(c, K_LAGCORR_LS);
+        lagcorr_kernel<LC_TI, LC_TD><<<dim3(g.nchunk, 2), g.threads, g.smem, c->stream>>>(p);
+    }
+    TRY(check_launch("lagcorr_kernel(ls)"));
+
+    LevinsonParams lp{};
+    lp.partial = c->partial.as<float2>();
+    lp.nchunk = g.nchunk;
+    lp.HT = g.HT;
+    lp.M = M;
+    lp.reg = reg;
+    lp.taps = c->lstaps.as<float2>();
+    lp.status = c->status.as<int>();
+    {
+        ProfScope ps(c, K_LEVINSON);
+        levinson_kernel<<<1, 256, (size_t)5 * M * sizeof(double2), c->stream>>>(lp);
+    }
+    TRY(check_launch("levinson_kernel"));
+
+    FirParams fp{};
+    fp.ref = ref; fp.srv = srv; fp.taps = c->lstaps.as<float2>(); fp.out = out;
+    fp.n = (int)n; fp.M = M; fp.peek = peek;
+    fp.Mpad = ceil_div(M, FIR_TK) * FIR_TK;
+    const int LO = FIR_THREADS * FIR_TO;
+    const size_t sm = (size_t)(fp.Mpad + LO + fp.Mpad) * sizeof(float2);
+    if (sm > SMEM_LIMIT) return fail(PRC_E_INVALID, "%d taps exceed the FIR kernel's shared memory", M);
+    {
+        ProfScope ps(c, K_FIR);
+        fir_apply_kernel<FIR_TK, FIR_TO><<<ceil_div(n, LO), FIR_THREADS, sm, c->stream>>>(fp);
+    }
+    TRY(check_launch("fir_apply_kernel"));
+    if (taps_out)
+        CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)M * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+    return PRC_OK;
+}
+
+int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek, float mu,
+                int block_len, const float2* init, float2* out, float2* taps_out) {
+    if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
+    if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
+        return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
+    if (block_len < 1) return fail(PRC_E_INVALID, "block_len=%d invalid", block_len);
+    const int M = filter_len + peek;
+    if (M > 1024 * NLMS_MAXT) return fail(PRC_E_INVALID, "%d taps exceed the NLMS kernel's maximum of %d", M, 1024 * NLMS_MAXT);
+    NlmsParams p{};
+    p.ref = ref; p.srv = srv; p.init = init; p.out = out; p.taps_out = taps_out;
+    p.n = (int)n; p.filter_len = filter_len; p.peek = peek; p.mu = mu; p.block_len = block_len;
+    const int kt = M <= 1024 ? 1 : (M <= 2048 ? 2 : 4);
+    const int threads = std::min(1024, ((ceil_div(M, kt) + 31) / 32) * 32);
+    const size_t sm = (size_t)(NLMS_TILE + ((M + 1) & ~1) + NLMS_TILE) * sizeof(float2) + 64 * sizeof(float4);
+    ProfScope ps(c, K_NLMS);
+    if (kt == 1) nlms_kernel<1><<<1, threads, sm, c->stream>>>(p);
+    else if (kt == 2) nlms_kernel<2><<<1, threads, sm, c->stream>>>(p);
+    else nlms_kernel<4><<<1, threads, sm, c->stream>>>(p);
+    return check_launch("nlms_kernel");
+}
+
+// window (host or device, double or float) -> device float
+int stage_window(Ctx* c, const void* window, long long n, int mem_kind, unsigned flags, const float** win32) {
+    *win32 = nullptr;
+    if (!window) return PRC_OK;
+    if (flags & PRC_FLAG_WINDOW_F32) {
+        if (mem_kind == PRC_MEM_DEVICE) {
+            *win32 = static_cast<const float*>(window);
+            return PRC_OK;
+        }
+        TRY(c->win32.ensure((size_t)n * sizeof(float)));
+        CU(cudaMemcpyAsync(c->win32.p, window, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        *win32 = c->win32.as<float>();
+        return PRC_OK;
+    }
+    const double* w64 = static_cast<const double*>(window);
+    TRY(c->win32.ensure((size_t)n * sizeof(float)));
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->win64.ensure((size_t)n * sizeof(double)));
+        CU(cudaMemcpyAsync(c->win64.p, window, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        w64 = c->win64.as<double>();
+    }
+    f64_to_f32_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(w64, c->win32.as<float>(), n);
+    TRY(check_launch("f64_to_f32_kernel"));
+    *win32 = c->win32.as<float>();
+    return PRC_OK;
+}
+
+int finish(Ctx* c, unsigned flags) {
+    if (flags & PRC_FLAG_ASYNC) return PRC_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    return PRC_OK;
+}
+
+int check_ls_status(Ctx* c, unsigned flags) {
+    if (flags & PRC_FLAG_ASYNC) return PRC_OK;   // caller owns the synchronisation; status stays on the device
+    int st = 0;
+    CU(cudaMemcpyAsync(&st, c->status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (st != 0) return fail(PRC_E_SINGULAR, "LS normal equations are not positive definite (singular Gram matrix)");
+    return PRC_OK;
+}
+
+bool bad_mem_kind(int k) { return k != PRC_MEM_HOST && k != PRC_MEM_DEVICE; }
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+int prc_version(void) { return PRC_VERSION; }
+
+const char* prc_last_error(void) { return g_err.c_str(); }
+
+int prc_device_count(int* count) {
+    if (!count) return fail(PRC_E_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(PRC_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return PRC_OK;
+}
+
+int prc_init(int device) {
+    Ctx* c;
+    return get_ctx(device, nullptr, &c);
+}
+
+void prc_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (Ctx* c : g_all_ctx) {
+        c->release();
+        delete c;
+    }
+    g_all_ctx.clear();
+    g_stream_ctx.clear();
+    g_epoch.fetch_add(1);
+}
+
+int prc_sync(int device, void* stream) {
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    CU(cudaStreamSynchronize(c->stream));
+    return PRC_OK;
+}
+
+uint64_t prc_launch_count(void) { return g_launches.load(); }
+
+int prc_profile_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return PRC_OK;
+}
+
+// Drains every workspace's pending event pairs (synchronising their streams) into the totals.
+int prc_profile_collect(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lp(g_prof_mu);
+    for (Ctx* c : g_all_ctx) {
+        std::lock_guard<std::mutex> lc(c->mu);
+        if (c->recs.empty()) continue;
+        cudaSetDevice(c->device);
+        for (ProfRec& r : c->recs) {
+            cudaEventSynchronize(r.b);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+                g_prof_ms[r.id] += ms;
+                g_prof_n[r.id] += 1;
+            }
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        c->recs.clear();
+    }
+    return PRC_OK;
+}
+
+int prc_profile_kernels(void) { return K_COUNT; }
+
+int prc_profile_read(int idx, const char** name, double* total_ms, uint64_t* launches) {
+    if (idx < 0 || idx >= K_COUNT) return fail(PRC_E_INVALID, "kernel index %d out of range", idx);
+    std::lock_guard<std::mutex> lp(g_prof_mu);
+    if (name) *name = kKernelNames[idx];
+    if (total_ms) *total_ms = g_prof_ms[idx];
+    if (launches) *launches = g_prof_n[idx];
+    return PRC_OK;
+}
+
+int prc_profile_reset(void) {
+    std::lock_guard<std::mutex> lp(g_prof_mu);
+    for (int i = 0; i < K_COUNT; ++i) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
+    return PRC_OK;
+}
+
+int prc_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return fail(PRC_E_INVALID, "ptr is NULL");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return PRC_OK;
+}
+int prc_host_free(void* ptr) {
+    CU(cudaFreeHost(ptr));
+    return PRC_OK;
+}
+int prc_host_register(void* ptr, uint64_t bytes) {
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return PRC_OK;
+}
+int prc_host_unregister(void* ptr) {
+    CU(cudaHostUnregister(ptr));
+    return PRC_OK;
+}
+
+int prc_xambg_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int range_bins, int freq_bins,
+                  const void* window, const double* dtaps, int64_t ndtaps, prc_c64* out, int mem_kind,
+                  int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (dtaps && ndtaps < 1) return fail(PRC_E_INVALID, "ndtaps=%lld invalid", (long long)ndtaps);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const size_t ob = (size_t)freq_bins * (range_bins + 1) * sizeof(float2);
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    float2* dout = reinterpret_cast<float2*>(out);
+    if (mem_kind == PRC_MEM_HOST) {
+        if (freq_bins < 1 || range_bins < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", freq_bins, range_bins);
+        TRY(c->ref.ensure(nb));
+        TRY(c->srv.ensure(nb));
+        TRY(c->out.ensure(ob));
+        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dout = c->out.as<float2>();
+    }
+    const float* win32;
+    TRY(stage_window(c, window, n, mem_kind, flags, &win32));
+    const float* taps32 = nullptr;
+    if (dtaps) {
+        TRY(c->dtaps32.ensure((size_t)ndtaps * sizeof(float)));
+        const double* t64 = dtaps;
+        if (mem_kind == PRC_MEM_HOST) {
+            TRY(c->dtaps64.ensure((size_t)ndtaps * sizeof(double)));
+            CU(cudaMemcpyAsync(c->dtaps64.p, dtaps, (size_t)ndtaps * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            t64 = c->dtaps64.as<double>();
+        }
+        f64_to_f32_kernel<<<ceil_div(ndtaps, 256), 256, 0, c->stream>>>(t64, c->dtaps32.as<float>(), ndtaps);
+        TRY(check_launch("f64_to_f32_kernel"));
+        taps32 = c->dtaps32.as<float>();
+    }
+    TRY(xambg_device(c, dref, dsrv, n, range_bins, freq_bins, win32, taps32, ndtaps, dout));
+    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, c->out.p, ob, cudaMemcpyDeviceToHost, c->stream));
+    return finish(c, flags);
+}
+
+int prc_ls_filter_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek, float reg,
+                      prc_c64* out, prc_c64* taps, int mem_kind, int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    float2* dout = reinterpret_cast<float2*>(out);
+    float2* dtaps = reinterpret_cast<float2*>(taps);
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->ref.ensure(nb));
+        TRY(c->srv.ensure(nb));
+        TRY(c->clean.ensure(nb));
+        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dout = c->clean.as<float2>();
+        dtaps = nullptr;
+    }
+    TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dout, dtaps));
+    if (mem_kind == PRC_MEM_HOST) {
+        CU(cudaMemcpyAsync(out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (taps)
+            CU(cudaMemcpyAsync(taps, c->lstaps.p, (size_t)(filter_len + peek) * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    }
+    TRY(check_ls_status(c, flags));
+    return finish(c, flags);
+}
+
+int prc_nlms_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek, float mu,
+                 int block_len, const prc_c64* init_taps, prc_c64* out, prc_c64* taps_out, int mem_kind,
+                 int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const int M = filter_len + peek;
+    const size_t mb = (size_t)(M > 0 ? M : 1) * sizeof(float2);
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    const float2* dinit = reinterpret_cast<const float2*>(init_taps);
+    float2* dout = reinterpret_cast<float2*>(out);
+    float2* dtaps = reinterpret_cast<float2*>(taps_out);
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->ref.ensure(nb));
+        TRY(c->srv.ensure(nb));
+        TRY(c->clean.ensure(nb));
+        TRY(c->nl_taps.ensure(mb));
+        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        if (init_taps) {
+            TRY(c->nl_init.ensure(mb));
+            CU(cudaMemcpyAsync(c->nl_init.p, init_taps, mb, cudaMemcpyHostToDevice, c->stream));
+            dinit = c->nl_init.as<float2>();
+        }
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dout = c->clean.as<float2>();
+        dtaps = c->nl_taps.as<float2>();
+    }
+    TRY(nlms_device(c, dref, dsrv, n, filter_len, peek, mu, block_len, dinit, dout, dtaps));
+    if (mem_kind == PRC_MEM_HOST) {
+        CU(cudaMemcpyAsync(out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (taps_out) CU(cudaMemcpyAsync(taps_out, c->nl_taps.p, mb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return finish(c, flags);
+}
+
+int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek, float reg,
+                  int range_bins, int freq_bins, const void* window, prc_c64* out_map, prc_c64* taps_out,
+                  prc_c64* cleaned_out, int mem_kind, int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out_map) return fail(PRC_E_INVALID, "ref/srv/out_map must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (freq_bins < 1 || range_bins < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", freq_bins, range_bins);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const size_t ob = (size_t)freq_bins * (range_bins + 1) * sizeof(float2);
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    float2* dmap = reinterpret_cast<float2*>(out_map);
+    float2* dtaps = reinterpret_cast<float2*>(taps_out);
+    TRY(c->clean.ensure(nb));
+    float2* dclean = c->clean.as<float2>();
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->ref.ensure(nb));
+        TRY(c->srv.ensure(nb));
+        TRY(c->out.ensure(ob));
+        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dmap = c->out.as<float2>();
+        dtaps = nullptr;
+    } else if (cleaned_out) {
+        dclean = reinterpret_cast<float2*>(cleaned_out);
+    }
+    const float* win32;
+    TRY(stage_window(c, window, n, mem_kind, flags, &win32));
+    TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dclean, dtaps));
+    TRY(xambg_device(c, dref, dclean, n, range_bins, freq_bins, win32, nullptr, 0, dmap));
+    if (mem_kind == PRC_MEM_HOST) {
+        CU(cudaMemcpyAsync(out_map, c->out.p, ob, cudaMemcpyDeviceToHost, c->stream));
+        if (taps_out)
+            CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)(filter_len + peek) * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+        if (cleaned_out) CU(cudaMemcpyAsync(cleaned_out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
+    }
+    TRY(check_ls_status(c, flags));
+    return finish(c, flags);
+}
+
+}  // extern "C"

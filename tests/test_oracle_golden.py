@@ -107,3 +107,21 @@ def test_shape_mismatch_raises_like_reference():
         xo.fast_xambg_oracle(a, b, 2, 2)
     with pytest.raises(ValueError, match="same length"):
         co.ls_filter_oracle(a, b, 2)
+
+
+@pytest.mark.parametrize("name", G.NLMS_ALL)
+def test_c_nlms_oracle_matches_reference(name):
+    g = G.load(name)
+    init = g["init"] if g["init"].shape[0] else None
+    out, w = co.block_nlms_oracle_c(g["ref"], g["srv"], int(g["filter_len"]), float(g["mu"]),
+                                    int(g["peek"]), 1, init)
+    assert G.rel_inf(out, g["out"]) < 2e-6
+    assert G.rel_inf(w, g["taps"]) < 2e-5
+
+
+def test_c_block_nlms_matches_python_definition():
+    g = G.load("nlms_small")
+    a, wa = co.block_nlms_oracle_c(g["ref"], g["srv"], int(g["filter_len"]), float(g["mu"]), int(g["peek"]), 16)
+    b, wb = co.block_nlms_oracle(g["ref"], g["srv"], int(g["filter_len"]), float(g["mu"]), int(g["peek"]), 16,
+                                 None, True)
+    assert G.rel_inf(a, b) < 2e-6 and G.rel_inf(wa, wb) < 2e-5
