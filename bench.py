@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- CPI frames/s of the passive-radar hot path (LS_Filter -> fast_xambg) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU oracle port on host cores
+
+One "step" = one batch of ``--batch`` CPI frames of BASELINE config 2 (2**20 samples, 256
+Doppler x 300 range, LS_Filter with filterLen = 300, reg = 1, peek = 10, Kaiser(5) window) pushed
+through the frame pipeline.  ``value`` = frames/s with the frames already resident in HBM (the
+batch is 268 MB, larger than the 126 MB L2, so no step finds its inputs cached); ``e2e`` = the
+same through ``FramePipeline.run_host`` with pinned HOST buffers, H2D of both channels and D2H of
+the map inside the timed region.  Rank r processes its own frames (weak scaling, no data-path
+collective); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1] / [2]: the configuration the metric is quoted on
+    "c2": dict(n=2 ** 20, F=256, R=300, filter_len=300, peek=10, reg=1.0,
+               name="1M-sample CPI (2^20), 256 Doppler x 300 range, LS_Filter(filterLen=300, reg=1, peek=10) -> fast_xambg(kaiser 5.0)"),
+    # BASELINE.json configs[0]: the reference's CPU-runnable plumbing case
+    "c1": dict(n=200_000, F=64, R=100, filter_len=100, peek=10, reg=1.0,
+               name="200k-sample CPI, 64 Doppler x 100 range, LS_Filter -> fast_xambg"),
+}
+METRIC = "CPI frames/sec (1M-sample CPI, 256 Doppler x 300 range)"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=16, help="frames per step")
+    ap.add_argument("--slots", type=int, default=4, help="concurrent frame slots (CUDA streams)")
+    ap.add_argument("--profile", default="P1", choices=["P0", "P1"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU arm (0 = auto)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- bytes / flops
+def bytes_frame(n, F, R):
+    """Compulsory HBM bytes per frame: read ref+srv once, write the map once."""
+    return 2 * 8 * n + 8 * F * (R + 1)
+
+
+def kernel_alg_bytes(cfg):
+    """Algorithmic bytes per launch for each kernel of the frame."""
+    n, F, R = cfg["n"], cfg["F"], cfg["R"]
+    M = cfg["filter_len"] + cfg["peek"]
+    return {
+        "lagcorr_ls": 2 * 8 * n + 2 * 8 * M,        # read ref, srv; write 2 x M correlation lags
+        "levinson": 2 * 8 * M + 8 * M,
+        "fir_apply": 3 * 8 * n,                     # read ref, srv; write cleaned srv
+        "lagcorr_caf": 2 * 8 * n + 4 * n + 8 * F * (R + 1),   # ref, cleaned srv, f32 window; block sums
+        "doppler_fft": 2 * 8 * F * (R + 1),
+    }
+
+
+def kernel_alg_flops(cfg):
+    n, F, R = cfg["n"], cfg["F"], cfg["R"]
+    M = cfg["filter_len"] + cfg["peek"]
+    return {"lagcorr_ls": 2 * 8 * n * M, "fir_apply": 8 * n * M, "lagcorr_caf": 8 * n * (R + 1)}
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def _cpu_sample_worker(args):
+    """One bounded sample of the frame on the CPU oracle (TEST INFRASTRUCTURE used as the timed
+    CPU baseline): LS_Filter on n/ls_div samples with the full tap count, fast_xambg on the full
+    frame for nlag_sub of the R+1 lags.  Returns the estimated seconds for one whole frame."""
+    cfg, seed_frame, ls_div, nlag_sub, profile = args
+    import scipy.signal as signal
+    from oracle import clutter_oracle as co
+    from oracle import xambg_oracle as xo
+    from passiveradar_b200 import synth
+    n, F, R = cfg["n"], cfg["F"], cfg["R"]
+    ref, srv = synth.make_frame(n, profile, seed_frame)
+    w = signal.get_window(("kaiser", 5.0), n)
+    ns = n // ls_div
+    t0 = time.perf_counter()
+    co.ls_filter_oracle(ref[:ns], srv[:ns], cfg["filter_len"], cfg["reg"], cfg["peek"])
+    t_ls = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    xo.fast_xambg_oracle(ref, srv, nlag_sub - 1, F, n, w)
+    t_x = time.perf_counter() - t0
+    return t_ls * ls_div + t_x * (R + 1) / nlag_sub, t_ls, t_x
+
+
+class CpuArm:
+    """Frame-parallel pool, one process per host core (OPENBLAS_NUM_THREADS=1), as SURVEY 8d asks."""
+
+    def __init__(self, cfg, procs, profile, rounds=1):
+        import multiprocessing as mp
+        self.cfg = cfg
+        self.profile = profile
+        ncpu = os.cpu_count() or 1
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            pass
+        # bounded sample, sized so that `rounds` rounds finish in ~2 minutes (a round with the
+        # 1/16 sample takes ~10 s on 8 cores: page-fault bound 160 MB data matrices)
+        div = 16
+        while div < 256 and rounds * 160.0 / div > 120.0:
+            div *= 2
+        self.ls_div = div if cfg["n"] >= 2 ** 19 else 1
+        self.nlag_sub = max(1, (cfg["R"] + 1) // div) if cfg["n"] >= 2 ** 19 else cfg["R"] + 1
+        # ~1 GB per worker at the bounded sample; cap by cores and by memory
+        try:
+            mem_gb = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+        except (ValueError, OSError):
+            mem_gb = 16
+        self.procs = procs if procs > 0 else max(1, min(ncpu, int(mem_gb // 2), 64))
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+        os.environ["OMP_NUM_THREADS"] = "1"
+        os.environ["MKL_NUM_THREADS"] = "1"
+        self.pool = mp.get_context("spawn").Pool(self.procs)
+        self.round = 0
+
+    def step(self):
+        """One round: every worker processes one bounded sample.  Returns (frames_equiv, seconds)."""
+        jobs = [(self.cfg, 1000 + self.round * self.procs + i, self.ls_div, self.nlag_sub, self.profile)
+                for i in range(self.procs)]
+        self.round += 1
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_sample_worker, jobs)
+        wall = time.perf_counter() - t0
+        est = [r[0] for r in res]
+        sampled = [r[1] + r[2] for r in res]
+        # whole-frame throughput of the pool = procs / (mean estimated whole-frame seconds), corrected
+        # by how much slower the round ran than its slowest worker's own compute (pool overhead)
+        eff = max(sampled) / wall if wall > 0 else 1.0
+        fps = self.procs / float(np.mean(est)) * min(1.0, eff)
+        return fps, wall, float(np.mean(est))
+
+    def sample_text(self):
+        c = self.cfg
+        return (f"per worker: LS_Filter oracle on n/{self.ls_div}={c['n'] // self.ls_div} samples x {c['filter_len'] + c['peek']} taps "
+                f"(time x{self.ls_div}) + fast_xambg oracle (shimmed decimate) on the full {c['n']}-sample frame for "
+                f"{self.nlag_sub} of {c['R'] + 1} lags (time x{(c['R'] + 1) / self.nlag_sub:.2f}); {self.procs} workers in parallel, "
+                f"1 BLAS thread each")
+
+    def close(self):
+        self.pool.terminate()
+        self.pool.join()
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    arm = CpuArm(cfg, args.cpu_procs, args.profile, rounds=args.steps + args.warmup)
+    try:
+        for _ in range(args.warmup):
+            arm.step()
+        fps_list, wall = [], 0.0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fps, w, _ = arm.step()
+            fps_list.append(fps)
+            wall += w
+        total = time.perf_counter() - t0
+    finally:
+        arm.close()
+    value = float(np.mean(fps_list))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; f64 block sums)",
+        "data": "synthetic", "config": {"workload": cfg["name"], "profile": args.profile},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": "port",
+                         "sample": arm.sample_text()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from passiveradar_b200 import _lib, synth
+    from passiveradar_b200.frames import FramePipeline, pinned_empty
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: libprcore has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, F, R = cfg["n"], cfg["F"], cfg["R"]
+    B = args.batch
+    pipe = FramePipeline(n, R, F, filter_len=cfg["filter_len"], reg=cfg["reg"], peek=cfg["peek"],
+                         window=("kaiser", 5.0), device=local_rank, nslots=args.slots)
+
+    # synthetic frames (host, pinned) -- rank r owns frames r*B .. r*B+B-1 of the stream
+    ref_h = pinned_empty((B, n))
+    srv_h = pinned_empty((B, n))
+    for i in range(B):
+        r, s = synth.make_frame(n, args.profile, rank * B + i)
+        ref_h[i] = r
+        srv_h[i] = s
+    ref_d = torch.from_numpy(ref_h).to(dev)
+    srv_d = torch.from_numpy(srv_h).to(dev)
+    maps_d = torch.empty((B, F, R + 1), dtype=torch.complex64, device=dev)
+    maps_h = pinned_empty((B, F, R + 1, 1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput (headline `value`)
+    for _ in range(max(args.warmup, 3)):
+        pipe.run_device(ref_d, srv_d, maps_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pipe.run_device(ref_d, srv_d, maps_d)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    frames_total = B * args.steps * world
+    value = frames_total / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
+    for _ in range(2):
+        pipe.run_host(ref_h, srv_h, maps_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe.run_host(ref_h, srv_h, maps_h)      # synchronises its streams before returning
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = frames_total / e2e_s
+
+    # ---- per-kernel durations: CUDA events on the launching stream, one frame at a time on one stream
+    roofline = None
+    per_kernel = {}
+    if rank == 0:
+        single = FramePipeline(n, R, F, filter_len=cfg["filter_len"], reg=cfg["reg"], peek=cfg["peek"],
+                               window=("kaiser", 5.0), device=local_rank, nslots=1)
+        single.run_device(ref_d[:2], srv_d[:2], maps_d[:2])
+        torch.cuda.synchronize(dev)
+        _lib.profile_reset()
+        _lib.profile(True)
+        reps = max(1, min(4, args.steps))
+        for _ in range(reps):
+            single.run_device(ref_d, srv_d, maps_d)     # B frames back to back, inputs > L2
+        torch.cuda.synchronize(dev)
+        prof = _lib.profile_read()
+        _lib.profile(False)
+        peaks = load_peaks()
+        algb = kernel_alg_bytes(cfg)
+        algf = kernel_alg_flops(cfg)
+        tot = sum(v[0] for v in prof.values())
+        for name, (tms, cnt) in prof.items():
+            if cnt == 0:
+                continue
+            avg_us = 1e3 * tms / cnt
+            per_kernel[name] = {"avg_us": round(avg_us, 3), "launches": cnt, "share": round(tms / tot, 4) if tot else None,
+                                "alg_GBps": round(algb.get(name, 0) / (avg_us * 1e-6) / 1e9, 2) if name in algb else None,
+                                "alg_TFLOPs": round(algf[name] / (avg_us * 1e-6) / 1e12, 2) if name in algf else None}
+        dom = max((k for k in per_kernel if k in algb), key=lambda k: prof[k][0])
+        ach = per_kernel[dom]["alg_GBps"]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": None, "peak_source": peaks["source"],
+                    "avg_launch_us": per_kernel[dom]["avg_us"],
+                    "fp32_TFLOPs": per_kernel[dom]["alg_TFLOPs"],
+                    "note": "direct-form lag correlation: 8*N*M flop per 16*N bytes (145+ flop/B) => FP32-pipe bound, not HBM bound; see DESIGN.md section 4",
+                    "frame_GBps": round(bytes_frame(n, F, R) * value / world / 1e9, 2)}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(cfg, args.cpu_procs, args.profile)
+        try:
+            fps, wall, est = arm.step()
+            cpu = {"value": fps, "unit": UNIT, "cores": arm.procs, "kind": "port", "sample": arm.sample_text(),
+                   "est_seconds_per_frame_per_core": est, "wall_s": wall}
+        finally:
+            arm.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; f64 Toeplitz solve)", "data": "synthetic",
+            "config": {"workload": cfg["name"], "frames_per_step_per_gpu": B, "slots": args.slots,
+                       "profile": args.profile, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                       "cache": f"inputs {B * 2 * n * 8 / 2 ** 20:.0f} MiB per step > 126 MB L2 (no flush needed)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 2 * n * 8,
+                    "d2h_bytes_per_step": B * F * (R + 1) * 8,
+                    "api": "passiveradar_b200.frames.FramePipeline.run_host (pinned host ndarrays)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": per_kernel,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "source": "MEASURED_PEAKS.json (measured copy bandwidth)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def main():
+    args = parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+    run_b200(args, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

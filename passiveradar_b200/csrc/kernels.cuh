@@ -86,6 +86,54 @@ __device__ __forceinline__ void slide_mac(float2 (&acc)[TD], const float2* __res
     }
 }
 
+// Packed variant: the same sliding-window MAC issued as FFMA2 (fma.rn.f32x2, sm_100+).  With
+//   A1[v] += (xr, xr) * (wr, wi)      A2[v] += (xi, xi) * (wr, wi)
+// every operand is an aligned 64-bit register pair, which (i) halves the instruction count and
+// (ii) removes the even/odd register-bank conflicts that cost the scalar FFMA form ~40 % of its
+// issue slots (ncu: dispatch_stall dominant, profiles/r01_lagcorr_v0.md).  The caller combines
+//   x*conj(w): re = A1.x + A2.y, im = A2.x - A1.y        x*w: re = A1.x - A2.y, im = A1.y + A2.x
+// xs4[i] = (xr, xr, xi, xi) of sample i (one broadcast 128-bit load per sample).
+template <int TI, int TD>
+__device__ __forceinline__ void slide_mac2(float2 (&A1)[TD], float2 (&A2)[TD], const float4* __restrict__ xs4,
+                                           const float2* __restrict__ ws, int nsteps) {
+    static_assert(TI % 2 == 0 && TD % 2 == 0, "128-bit shared loads need even tile sizes");
+    constexpr int RS = TI + TD;
+    constexpr int PERIOD = RS / Gcd<RS, TI>::v;
+    static_assert(PERIOD <= 4, "unroll factor too large for the instruction cache");
+    float2 W[RS];
+#pragma unroll
+    for (int q = 0; q < TD; q += 2) {
+        const float4 v = *reinterpret_cast<const float4*>(ws + q);
+        W[q] = make_float2(v.x, v.y);
+        W[q + 1] = make_float2(v.z, v.w);
+    }
+    for (int t0 = 0; t0 < nsteps; t0 += PERIOD) {
+#pragma unroll
+        for (int p = 0; p < PERIOD; ++p) {
+            if (t0 + p < nsteps) {
+                const float2* wp = ws + (t0 + p) * TI + TD;
+                const float4* xp = xs4 + (t0 + p) * TI;
+#pragma unroll
+                for (int q = 0; q < TI; q += 2) {
+                    const float4 v = *reinterpret_cast<const float4*>(wp + q);
+                    W[(p * TI + TD + q) % RS] = make_float2(v.x, v.y);
+                    W[(p * TI + TD + q + 1) % RS] = make_float2(v.z, v.w);
+                }
+#pragma unroll
+                for (int u = 0; u < TI; ++u) {
+                    const float4 xv = xp[u];
+                    const float2 xr2 = make_float2(xv.x, xv.y);
+                    const float2 xi2 = make_float2(xv.z, xv.w);
+#pragma unroll
+                    for (int v = 0; v < TD; ++v) A1[v] = __ffma2_rn(xr2, W[(p * TI + u + v) % RS], A1[v]);
+#pragma unroll
+                    for (int v = 0; v < TD; ++v) A2[v] = __ffma2_rn(xi2, W[(p * TI + u + v) % RS], A2[v]);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // lagcorr: partial[prob][blk][chunk][l] = sum_{i in chunk of block blk} xw[i] * conj(s[(i + dmin + l) mod n])
 //   xw[i] = x[i] * win[i] * taps[blk_hi - i]   (either factor optional), 0 outside [0, n)
@@ -110,7 +158,8 @@ struct LagCorrParams {
     float2* partial;
 };
 
-template <int TI, int TD>
+// PACKED: x is staged as (xr, xr, xi, xi) float4 and the MACs are FFMA2 (slide_mac2)
+template <int TI, int TD, bool PACKED>
 __global__ void __launch_bounds__(512) lagcorr_kernel(const __grid_constant__ LagCorrParams p) {
     extern __shared__ __align__(16) float2 smem[];
     const int tid = threadIdx.x;
@@ -121,8 +170,9 @@ __global__ void __launch_bounds__(512) lagcorr_kernel(const __grid_constant__ La
     const int Sg = p.steps * TI;
     const int Lpad = p.G * Sg;
     const int HT = p.H * TD;
+    constexpr int XW = PACKED ? 2 : 1;      // float2 slots per staged x sample
     float2* xs = smem;
-    float2* ss = smem + Lpad;
+    float2* ss = smem + XW * Lpad;
 
     const long long blk_lo = p.blk_first_lo + (long long)blk * p.blk_stride;
     const long long blk_hi = blk_lo + p.blk_len - 1;
@@ -130,17 +180,35 @@ __global__ void __launch_bounds__(512) lagcorr_kernel(const __grid_constant__ La
     int len = p.blk_len - chunk * p.chunk_len;
     if (len > p.chunk_len) len = p.chunk_len;
 
+    // Staging issues STAGE_BATCH independent global loads per thread before the first store:
+    // a one-load-per-iteration loop serialises ~16 DRAM latencies per CTA (measured: 30 % of the
+    // kernel, profiles/r01_lagcorr_v1.md).
+    constexpr int STAGE_BATCH = 8;
     // ---- stage the weighted x chunk (zero outside the block / the signal)
     const float2* __restrict__ x = p.x;
-    for (int q = tid; q < Lpad; q += nthr) {
-        float2 v = make_float2(0.f, 0.f);
-        const long long i = chunk_lo + q;
-        if (q < len && i >= 0 && i < p.n) {
-            v = x[i];
-            if (p.win) { const float w = p.win[i]; v.x *= w; v.y *= w; }
-            if (p.taps) { const float w = p.taps[blk_hi - i]; v.x *= w; v.y *= w; }
+    for (int base = 0; base < Lpad; base += nthr * STAGE_BATCH) {
+        float2 v[STAGE_BATCH];
+        float w[STAGE_BATCH];
+#pragma unroll
+        for (int b = 0; b < STAGE_BATCH; ++b) {
+            const int q = base + b * nthr + tid;
+            const long long i = chunk_lo + q;
+            const bool ok = q < len && i >= 0 && i < p.n;
+            v[b] = ok ? x[i] : make_float2(0.f, 0.f);
+            w[b] = 1.f;
+            if (p.win && ok) w[b] = p.win[i];
+            if (p.taps && ok) w[b] *= p.taps[blk_hi - i];
         }
-        xs[q] = v;
+#pragma unroll
+        for (int b = 0; b < STAGE_BATCH; ++b) {
+            const int q = base + b * nthr + tid;
+            if (q < Lpad) {
+                float2 t = v[b];
+                if (p.win || p.taps) { t.x *= w[b]; t.y *= w[b]; }
+                if (PACKED) reinterpret_cast<float4*>(xs)[q] = make_float4(t.x, t.x, t.y, t.y);
+                else xs[q] = t;
+            }
+        }
     }
     // ---- stage the circular window of s that the chunk's lags touch
     const float2* __restrict__ s = p.s[prob];
@@ -149,10 +217,21 @@ __global__ void __launch_bounds__(512) lagcorr_kernel(const __grid_constant__ La
         if (s0 < 0) s0 += p.n;
         const unsigned start = (unsigned)s0;
         const unsigned n = (unsigned)p.n;
-        for (int q = tid; q < Lpad + HT; q += nthr) {
-            unsigned idx = start + (unsigned)q;
-            if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }
-            ss[q] = s[idx];
+        const int cnt = Lpad + HT;
+        for (int base = 0; base < cnt; base += nthr * STAGE_BATCH) {
+            float2 v[STAGE_BATCH];
+#pragma unroll
+            for (int b = 0; b < STAGE_BATCH; ++b) {
+                const int q = base + b * nthr + tid;
+                unsigned idx = start + (unsigned)q;
+                if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }
+                v[b] = (q < cnt) ? s[idx] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int b = 0; b < STAGE_BATCH; ++b) {
+                const int q = base + b * nthr + tid;
+                if (q < cnt) ss[q] = v[b];
+            }
         }
     }
     __syncthreads();
@@ -163,7 +242,18 @@ __global__ void __launch_bounds__(512) lagcorr_kernel(const __grid_constant__ La
     const int h = tid % p.H;
     const int g = tid / p.H;
     const bool active = g < p.G;
-    if (active) slide_mac<TI, TD, true>(acc, xs + g * Sg, ss + g * Sg + h * TD, p.steps);
+    if (active) {
+        if (PACKED) {
+            float2 A1[TD], A2[TD];
+#pragma unroll
+            for (int v = 0; v < TD; ++v) { A1[v] = make_float2(0.f, 0.f); A2[v] = make_float2(0.f, 0.f); }
+            slide_mac2<TI, TD>(A1, A2, reinterpret_cast<const float4*>(xs) + g * Sg, ss + g * Sg + h * TD, p.steps);
+#pragma unroll
+            for (int v = 0; v < TD; ++v) acc[v] = make_float2(A1[v].x + A2[v].y, A2[v].x - A1[v].y);
+        } else {
+            slide_mac<TI, TD, true>(acc, xs + g * Sg, ss + g * Sg + h * TD, p.steps);
+        }
+    }
     __syncthreads();
 
     // ---- reduce the G sample groups in a fixed order (deterministic), write the partial row
@@ -200,19 +290,22 @@ struct FirParams {
     int peek;
 };
 
-template <int TK, int TO>
+template <int TK, int TO, bool PACKED>
 __global__ void __launch_bounds__(512) fir_apply_kernel(const __grid_constant__ FirParams p) {
     extern __shared__ __align__(16) float2 smem[];
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
     const int LO = nthr * TO;
-    float2* tr = smem;              // Mpad reversed taps
-    float2* rs = smem + p.Mpad;     // LO + Mpad window of ref
+    constexpr int XW = PACKED ? 2 : 1;
+    float2* tr = smem;                   // Mpad reversed taps ((tr, tr, ti, ti) when PACKED)
+    float2* rs = smem + XW * p.Mpad;     // LO + Mpad window of ref
     const long long I0 = (long long)blockIdx.x * LO;
 
     for (int q = tid; q < p.Mpad; q += nthr) {
         const int k = p.Mpad - 1 - q;
-        tr[q] = (k < p.M) ? p.taps[k] : make_float2(0.f, 0.f);
+        const float2 tv = (k < p.M) ? p.taps[k] : make_float2(0.f, 0.f);
+        if (PACKED) reinterpret_cast<float4*>(tr)[q] = make_float4(tv.x, tv.x, tv.y, tv.y);
+        else tr[q] = tv;
     }
     {
         long long r0 = (I0 + p.peek - (p.Mpad - 1)) % p.n;
@@ -220,10 +313,22 @@ __global__ void __launch_bounds__(512) fir_apply_kernel(const __grid_constant__ 
         const unsigned start = (unsigned)r0;
         const unsigned n = (unsigned)p.n;
         const float2* __restrict__ ref = p.ref;
-        for (int q = tid; q < LO + p.Mpad; q += nthr) {
-            unsigned idx = start + (unsigned)q;
-            if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }
-            rs[q] = ref[idx];
+        constexpr int STAGE_BATCH = 8;          // independent loads in flight per thread
+        const int cnt = LO + p.Mpad;
+        for (int base = 0; base < cnt; base += nthr * STAGE_BATCH) {
+            float2 v[STAGE_BATCH];
+#pragma unroll
+            for (int b = 0; b < STAGE_BATCH; ++b) {
+                const int q = base + b * nthr + tid;
+                unsigned idx = start + (unsigned)q;
+                if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }
+                v[b] = (q < cnt) ? ref[idx] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int b = 0; b < STAGE_BATCH; ++b) {
+                const int q = base + b * nthr + tid;
+                if (q < cnt) rs[q] = v[b];
+            }
         }
     }
     __syncthreads();
@@ -231,7 +336,16 @@ __global__ void __launch_bounds__(512) fir_apply_kernel(const __grid_constant__ 
     float2 acc[TO];
 #pragma unroll
     for (int v = 0; v < TO; ++v) acc[v] = make_float2(0.f, 0.f);
-    slide_mac<TK, TO, false>(acc, tr, rs + tid * TO, p.Mpad / TK);
+    if (PACKED) {
+        float2 A1[TO], A2[TO];
+#pragma unroll
+        for (int v = 0; v < TO; ++v) { A1[v] = make_float2(0.f, 0.f); A2[v] = make_float2(0.f, 0.f); }
+        slide_mac2<TK, TO>(A1, A2, reinterpret_cast<const float4*>(tr), rs + tid * TO, p.Mpad / TK);
+#pragma unroll
+        for (int v = 0; v < TO; ++v) acc[v] = make_float2(A1[v].x - A2[v].y, A1[v].y + A2[v].x);
+    } else {
+        slide_mac<TK, TO, false>(acc, tr, rs + tid * TO, p.Mpad / TK);
+    }
 
     const long long i0 = I0 + (long long)tid * TO;
 #pragma unroll
@@ -267,87 +381,168 @@ __device__ __forceinline__ double2 zmul(double2 a, double2 b) {
 __device__ __forceinline__ double2 zmulc(double2 a, double2 b) {   // a * conj(b)
     return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+// Inner-product-free (Schur-type) Levinson: besides the forward vector f and the solution w it
+// carries P = T[f;0], Q = T[b;0] (b = conj(reverse(f))) and the residual rho = rhs - T[w;0], so the
+// reflection coefficient of order n is simply P[n] and the solution increment is rho[n]; every
+// step is element-wise plus a one-element shift.  Thread tid owns elements
+// tid*E .. tid*E+E-1 in registers; one named-barrier sync per step; fp64 throughout.
+//   E = 1: blockDim 1024, M <= 1024        E = 4: blockDim 512, M <= 2048
+constexpr int LEV_SCRATCH = 4 + 2 * 32 * 2;     // double2: pivot[2][2] + edge[2][32][2]
+
+__host__ __device__ inline int levinson_nparts(int M, int threads) {
+    const int q = threads / (2 * M);
+    return q > 3 ? 3 : q;
+}
+__host__ __device__ inline size_t levinson_smem(int M, int threads) {
+    const int np = levinson_nparts(M, threads);
+    const int scratch = np * 2 * M > LEV_SCRATCH ? np * 2 * M : LEV_SCRATCH;
+    return (size_t)(2 * M + scratch) * sizeof(double2);
 }
 
-__global__ void __launch_bounds__(256) levinson_kernel(const __grid_constant__ LevinsonParams p) {
+template <int E>
+__global__ void __launch_bounds__(E == 1 ? 1024 : 512) levinson_kernel(const __grid_constant__ LevinsonParams p) {
     extern __shared__ __align__(16) double2 zs[];
     const int M = p.M;
-    double2* t = zs;            // Toeplitz first column (t[0] real, + reg)
-    double2* r = zs + M;        // right-hand side
-    double2* f0 = zs + 2 * M;   // forward vector (double buffered)
-    double2* f1 = zs + 3 * M;
-    double2* w = zs + 4 * M;    // solution
+    double2* t = zs;                  // M   Toeplitz first column (t[0] real, + reg)
+    double2* r = zs + M;              // M   right-hand side
+    double2* part = zs + 2 * M;       // phase-A partial sums, then reused as:
+    double2* pivot = part;            //   [2][2]      (P[n], rho[n]) double buffered
+    double2* edge = part + 4;         //   [2][32][2]  last (newQ, newb) of every warp
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
 
-    // phase A: fp64 sum over chunks (fixed order), conjugate
-    for (int m = tid; m < 2 * M; m += blockDim.x) {
-        const int prob = m / M;
-        const int l = m - prob * M;
-        const float2* src = p.partial + (size_t)prob * p.nchunk * p.HT + l;
-        double sx = 0.0, sy = 0.0;
-        for (int c = 0; c < p.nchunk; ++c) {
-            const float2 v = src[(size_t)c * p.HT];
-            sx += (double)v.x;
-            sy += (double)v.y;
+    // ---- phase A: fp64 sum of the chunk partials in a fixed order, conjugate
+    {
+        const int nval = 2 * M;
+        const int nparts = levinson_nparts(M, blockDim.x);
+        if (nparts > 0) {
+            const int pt = tid / nval, v = tid - pt * nval;
+            if (pt < nparts) {
+                const int prob = v / M, l = v - prob * M;
+                const float2* src = p.partial + (size_t)prob * p.nchunk * p.HT + l;
+                double sx = 0.0, sy = 0.0;
+#pragma unroll 8
+                for (int c = pt; c < p.nchunk; c += nparts) {
+                    const float2 q = src[(size_t)c * p.HT];
+                    sx += (double)q.x;
+                    sy += (double)q.y;
+                }
+                part[pt * nval + v] = make_double2(sx, sy);
+            }
+            __syncthreads();
         }
-        if (prob == 0) t[l] = make_double2(sx, -sy);
-        else r[l] = make_double2(sx, -sy);
+        double2 tot[(E == 1) ? 2 : 8];
+        int cnt = 0;
+        for (int v2 = tid; v2 < nval; v2 += blockDim.x, ++cnt) {
+            double sx = 0.0, sy = 0.0;
+            if (nparts > 0) {
+                for (int k = 0; k < nparts; ++k) { sx += part[k * nval + v2].x; sy += part[k * nval + v2].y; }
+            } else {
+                const int prob = v2 / M, l = v2 - prob * M;
+                const float2* src = p.partial + (size_t)prob * p.nchunk * p.HT + l;
+#pragma unroll 8
+                for (int c = 0; c < p.nchunk; ++c) {
+                    const float2 q = src[(size_t)c * p.HT];
+                    sx += (double)q.x;
+                    sy += (double)q.y;
+                }
+            }
+            tot[cnt] = make_double2(sx, -sy);
+        }
+        __syncthreads();                 // everyone is done reading `part` before t/r/pivot/edge are written
+        cnt = 0;
+        for (int v2 = tid; v2 < nval; v2 += blockDim.x, ++cnt) {
+            if (v2 < M) t[v2] = tot[cnt];
+            else r[v2 - M] = tot[cnt];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (tid >= 32) return;
-    const int lane = tid;
 
+    const int nact = ((M + E - 1) / E + 31) & ~31;      // threads taking part in the recursion
+    if (tid >= nact) return;
     const double t0 = t[0].x + p.reg;
     int bad = !(t0 > 0.0) || !isfinite(t0);
-    if (lane == 0) {
-        f0[0] = make_double2(1.0 / t0, 0.0);
-        w[0] = make_double2(r[0].x / t0, r[0].y / t0);
+    const double it0 = 1.0 / t0;
+
+    double2 P[E], Qs[E], rho[E], f[E], bs[E], x[E];
+    const double2 x0 = make_double2(r[0].x * it0, r[0].y * it0);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int j = tid * E + e;
+        const double2 zero = make_double2(0.0, 0.0);
+        const double2 tj = (j < M) ? (j == 0 ? make_double2(t0, 0.0) : t[j]) : zero;
+        const double2 tjm = (j >= 1 && j <= M) ? (j == 1 ? make_double2(t0, 0.0) : t[j - 1]) : zero;
+        const double2 rj = (j < M) ? r[j] : zero;
+        P[e] = make_double2(tj.x * it0, tj.y * it0);              // T[f;0],  f = [1/t0]
+        Qs[e] = make_double2(tjm.x * it0, tjm.y * it0);           // (T[b;0]) shifted down by one
+        f[e] = (j == 0) ? make_double2(it0, 0.0) : zero;
+        bs[e] = (j == 1) ? make_double2(it0, 0.0) : zero;         // b shifted down by one
+        x[e] = (j == 0) ? x0 : zero;
+        const double2 xt = zmul(x0, tj);
+        rho[e] = make_double2(rj.x - xt.x, rj.y - xt.y);          // rhs - T[x;0]
+        if (j == 1) { pivot[2] = P[e]; pivot[3] = rho[e]; }       // step n reads buffer n & 1
     }
-    __syncwarp();
-    double2* f = f0;
-    double2* fn = f1;
+    asm volatile("bar.sync 1, %0;" ::"r"(nact));
+
     for (int n = 1; n < M; ++n) {
-        // ef = sum_i t[n-i] f[i],  ex = sum_i t[n-i] w[i],  i = 0..n-1
-        double efx = 0, efy = 0, exx = 0, exy = 0;
-        for (int i = lane; i < n; i += 32) {
-            const double2 tv = t[n - i];
-            const double2 a = zmul(tv, f[i]);
-            const double2 b = zmul(tv, w[i]);
-            efx += a.x; efy += a.y; exx += b.x; exy += b.y;
-        }
-        efx = warp_sum(efx); efy = warp_sum(efy); exx = warp_sum(exx); exy = warp_sum(exy);
-        const double den = 1.0 - (efx * efx + efy * efy);
+        const int buf = n & 1;
+        const double2 ef = pivot[buf * 2 + 0];
+        const double2 d = pivot[buf * 2 + 1];
+        const double den = 1.0 - (ef.x * ef.x + ef.y * ef.y);
         if (!(den > 0.0) || !isfinite(den)) bad = 1;
-        const double inv = 1.0 / den;
-        const double2 ef = make_double2(efx, efy);
-        // fn[i] = ( f[i]*[i<n] - ef * conj(f[n-i])*[i>=1] ) / den ,  i = 0..n
-        for (int i = lane; i <= n; i += 32) {
-            double2 v = make_double2(0.0, 0.0);
-            if (i < n) v = f[i];
-            if (i >= 1) {
-                const double2 c = zmulc(ef, f[n - i]);
-                v.x -= c.x; v.y -= c.y;
+        const double al = 1.0 / den;
+        double2 nQ[E], nb[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int j = tid * E + e;
+            const double2 q0 = (j == 0) ? make_double2(ef.x, -ef.y) : Qs[e];
+            const double2 a = zmul(ef, q0);           // ef * Qs
+            const double2 b = zmulc(P[e], ef);        // conj(ef) * P
+            const double2 np = make_double2(al * (P[e].x - a.x), al * (P[e].y - a.y));
+            nQ[e] = make_double2(al * (q0.x - b.x), al * (q0.y - b.y));
+            const double2 c = zmul(ef, bs[e]);
+            const double2 g = zmulc(f[e], ef);        // conj(ef) * f
+            const double2 nf = make_double2(al * (f[e].x - c.x), al * (f[e].y - c.y));
+            nb[e] = make_double2(al * (bs[e].x - g.x), al * (bs[e].y - g.y));
+            const double2 dx = zmul(d, nb[e]);
+            x[e] = make_double2(x[e].x + dx.x, x[e].y + dx.y);
+            const double2 dq = zmul(d, nQ[e]);
+            rho[e] = make_double2(rho[e].x - dq.x, rho[e].y - dq.y);
+            P[e] = np;
+            f[e] = nf;
+            if (j == n + 1) { pivot[(buf ^ 1) * 2 + 0] = np; pivot[(buf ^ 1) * 2 + 1] = rho[e]; }
+        }
+        // shift by one element: (Qs, bs)[j] <- (nQ, nb)[j-1]
+        double2 inQ, inB;
+        inQ.x = __shfl_up_sync(0xffffffffu, nQ[E - 1].x, 1);
+        inQ.y = __shfl_up_sync(0xffffffffu, nQ[E - 1].y, 1);
+        inB.x = __shfl_up_sync(0xffffffffu, nb[E - 1].x, 1);
+        inB.y = __shfl_up_sync(0xffffffffu, nb[E - 1].y, 1);
+        if (lane == 31) {
+            edge[(buf * 32 + warp) * 2 + 0] = nQ[E - 1];
+            edge[(buf * 32 + warp) * 2 + 1] = nb[E - 1];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nact));
+        if (lane == 0) {
+            if (warp == 0) {
+                inQ = make_double2(0.0, 0.0);
+                inB = make_double2(0.0, 0.0);
+            } else {
+                inQ = edge[(buf * 32 + warp - 1) * 2 + 0];
+                inB = edge[(buf * 32 + warp - 1) * 2 + 1];
             }
-            fn[i] = make_double2(v.x * inv, v.y * inv);
         }
-        __syncwarp();
-        // w[i] += (r[n] - ex) * conj(fn[n-i]),  i = 0..n   (w[n] starts at 0)
-        const double2 dlt = make_double2(r[n].x - exx, r[n].y - exy);
-        for (int i = lane; i <= n; i += 32) {
-            const double2 c = zmulc(dlt, fn[n - i]);
-            double2 v = (i < n) ? w[i] : make_double2(0.0, 0.0);
-            v.x += c.x; v.y += c.y;
-            w[i] = v;
-        }
-        __syncwarp();
-        double2* tmp = f; f = fn; fn = tmp;
+#pragma unroll
+        for (int e = E - 1; e >= 1; --e) { Qs[e] = nQ[e - 1]; bs[e] = nb[e - 1]; }
+        Qs[0] = inQ;
+        bs[0] = inB;
     }
-    for (int i = lane; i < M; i += 32) p.taps[i] = make_float2((float)w[i].x, (float)w[i].y);
-    if (lane == 0) *p.status = bad;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int j = tid * E + e;
+        if (j < M) p.taps[j] = make_float2((float)x[e].x, (float)x[e].y);
+    }
+    if (tid == 0) *p.status = bad;
 }
 
 // ------------------------------------------------------------------------------------------

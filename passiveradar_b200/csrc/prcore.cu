@@ -126,6 +126,7 @@ std::vector<Ctx*> g_all_ctx;
 std::atomic<bool> g_attrs_set[64];
 std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
 int g_tune_nchunk = -1, g_tune_g = -1;
+int g_packed = 1;          // FFMA2 kernels (PRC_PACKED=0 selects the scalar-FFMA variant for A/B runs)
 std::once_flag g_env_once;
 
 struct TlsCtx {
@@ -137,14 +138,18 @@ thread_local TlsCtx g_tls;
 void read_env() {
     if (const char* e = getenv("PRC_TUNE_NCHUNK")) g_tune_nchunk = atoi(e);
     if (const char* e = getenv("PRC_TUNE_G")) g_tune_g = atoi(e);
+    if (const char* e = getenv("PRC_PACKED")) g_packed = atoi(e);
 }
 
 int set_kernel_attrs(int device) {
     if (g_attrs_set[device].load()) return PRC_OK;
     const int lim = (int)SMEM_LIMIT;
-    CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CU(cudaFuncSetAttribute(levinson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(levinson_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(levinson_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(doppler_fft_pow2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(doppler_fft_pow2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(doppler_fft_pow2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -258,7 +263,7 @@ int choose_geo(int blk_len, long long outer, int nlag, int nsm, Geo* g) {
         g->G = std::max(1, std::min(gmax, ceil_div(g->chunk_len, TI * 4)));
         g->steps = ceil_div(ceil_div(g->chunk_len, g->G), TI);
         const size_t Lpad = (size_t)g->G * g->steps * TI;
-        g->smem = std::max(2 * Lpad + g->HT, (size_t)g->G * g->HT) * sizeof(float2);
+        g->smem = std::max((g_packed ? 3 : 2) * Lpad + g->HT, (size_t)g->G * g->HT) * sizeof(float2);
         if (g->smem <= 100 * 1024 || g->chunk_len <= TI) break;
         nchunk = nchunk * 2;
     }
@@ -319,7 +324,9 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     p.partial = c->partial.as<float2>();
     {
         ProfScope ps(c, K_LAGCORR_CAF);
-        lagcorr_kernel<LC_TI, LC_TD><<<dim3((unsigned)((long long)F * g.nchunk), 1), g.threads, g.smem, c->stream>>>(p);
+        const dim3 grid((unsigned)((long long)F * g.nchunk), 1);
+        if (g_packed) lagcorr_kernel<LC_TI, LC_TD, true><<<grid, g.threads, g.smem, c->stream>>>(p);
+        else lagcorr_kernel<LC_TI, LC_TD, false><<<grid, g.threads, g.smem, c->stream>>>(p);
     }
     TRY(check_launch("lagcorr_kernel(caf)"));
 
@@ -370,7 +377,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
         return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
     const int M = filter_len + peek;
-    if ((size_t)5 * M * sizeof(double2) > SMEM_LIMIT) return fail(PRC_E_INVALID, "%d taps exceed the solver's shared memory", M);
+    if (M > 2048) return fail(PRC_E_INVALID, "%d taps exceed the Toeplitz solver's maximum of 2048", M);
     Geo g;
     TRY(choose_geo((int)n, 2, M, c->nsm, &g));
     TRY(c->partial.ensure((size_t)2 * g.nchunk * g.HT * sizeof(float2)));
@@ -393,7 +400,8 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     p.partial = c->partial.as<float2>();
     {
         ProfScope ps(c, K_LAGCORR_LS);
-        lagcorr_kernel<LC_TI, LC_TD><<<dim3(g.nchunk, 2), g.threads, g.smem, c->stream>>>(p);
+        if (g_packed) lagcorr_kernel<LC_TI, LC_TD, true><<<dim3(g.nchunk, 2), g.threads, g.smem, c->stream>>>(p);
+        else lagcorr_kernel<LC_TI, LC_TD, false><<<dim3(g.nchunk, 2), g.threads, g.smem, c->stream>>>(p);
     }
     TRY(check_launch("lagcorr_kernel(ls)"));
 
@@ -407,7 +415,8 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     lp.status = c->status.as<int>();
     {
         ProfScope ps(c, K_LEVINSON);
-        levinson_kernel<<<1, 256, (size_t)5 * M * sizeof(double2), c->stream>>>(lp);
+        if (M <= 1024) levinson_kernel<1><<<1, 1024, levinson_smem(M, 1024), c->stream>>>(lp);
+        else levinson_kernel<4><<<1, 512, levinson_smem(M, 512), c->stream>>>(lp);
     }
     TRY(check_launch("levinson_kernel"));
 
@@ -416,11 +425,12 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     fp.n = (int)n; fp.M = M; fp.peek = peek;
     fp.Mpad = ceil_div(M, FIR_TK) * FIR_TK;
     const int LO = FIR_THREADS * FIR_TO;
-    const size_t sm = (size_t)(fp.Mpad + LO + fp.Mpad) * sizeof(float2);
+    const size_t sm = (size_t)((g_packed ? 2 : 1) * fp.Mpad + LO + fp.Mpad) * sizeof(float2);
     if (sm > SMEM_LIMIT) return fail(PRC_E_INVALID, "%d taps exceed the FIR kernel's shared memory", M);
     {
         ProfScope ps(c, K_FIR);
-        fir_apply_kernel<FIR_TK, FIR_TO><<<ceil_div(n, LO), FIR_THREADS, sm, c->stream>>>(fp);
+        if (g_packed) fir_apply_kernel<FIR_TK, FIR_TO, true><<<ceil_div(n, LO), FIR_THREADS, sm, c->stream>>>(fp);
+        else fir_apply_kernel<FIR_TK, FIR_TO, false><<<ceil_div(n, LO), FIR_THREADS, sm, c->stream>>>(fp);
     }
     TRY(check_launch("fir_apply_kernel"));
     if (taps_out)
