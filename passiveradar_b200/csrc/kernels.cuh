@@ -23,6 +23,17 @@
 
 namespace prc {
 
+// stream decomposition used by lagstream_kernel and its consumers: block `blk` of length blk_len
+// starts at stream position blk*blk_len; CTA c owns [c*per_cta, (c+1)*per_cta)
+__host__ __device__ inline long long stream_first_cta(long long blk, int blk_len, long long per_cta) {
+    return (blk * (long long)blk_len) / per_cta;
+}
+__host__ __device__ inline int stream_pieces(long long blk, int blk_len, long long per_cta) {
+    const long long a = (blk * (long long)blk_len) / per_cta;
+    const long long b = ((blk + 1) * (long long)blk_len - 1) / per_cta;
+    return (int)(b - a + 1);
+}
+
 template <int A, int B> struct Gcd { static constexpr int v = Gcd<B, A % B>::v; };
 template <int A> struct Gcd<A, 0> { static constexpr int v = A; };
 
@@ -128,6 +139,53 @@ __device__ __forceinline__ void slide_mac2(float2 (&A1)[TD], float2 (&A2)[TD], c
                     for (int v = 0; v < TD; ++v) A1[v] = __ffma2_rn(xr2, W[(p * TI + u + v) % RS], A1[v]);
 #pragma unroll
                     for (int v = 0; v < TD; ++v) A2[v] = __ffma2_rn(xi2, W[(p * TI + u + v) % RS], A2[v]);
+                }
+            }
+        }
+    }
+}
+
+// FFMA2 sliding MAC with x in its natural (re, im) layout; the (xr, xr) / (xi, xi) operand pairs
+// are built in registers (moves go to the ALU pipe, whose issue slots the half-rate FFMA2 stream
+// leaves free).  Otherwise identical to slide_mac2.
+template <int TI, int TD>
+__device__ __forceinline__ void slide_mac2n(float2 (&A1)[TD], float2 (&A2)[TD], const float2* __restrict__ xs,
+                                            const float2* __restrict__ ws, int nsteps) {
+    static_assert(TI % 2 == 0 && TD % 2 == 0, "128-bit shared loads need even tile sizes");
+    constexpr int RS = TI + TD;
+    constexpr int PERIOD = RS / Gcd<RS, TI>::v;
+    static_assert(PERIOD <= 4, "unroll factor too large for the instruction cache");
+    float2 W[RS];
+#pragma unroll
+    for (int q = 0; q < TD; q += 2) {
+        const float4 v = *reinterpret_cast<const float4*>(ws + q);
+        W[q] = make_float2(v.x, v.y);
+        W[q + 1] = make_float2(v.z, v.w);
+    }
+    for (int t0 = 0; t0 < nsteps; t0 += PERIOD) {
+#pragma unroll
+        for (int p = 0; p < PERIOD; ++p) {
+            if (t0 + p < nsteps) {
+                const float2* wp = ws + (t0 + p) * TI + TD;
+                const float2* xp = xs + (t0 + p) * TI;
+#pragma unroll
+                for (int q = 0; q < TI; q += 2) {
+                    const float4 v = *reinterpret_cast<const float4*>(wp + q);
+                    W[(p * TI + TD + q) % RS] = make_float2(v.x, v.y);
+                    W[(p * TI + TD + q + 1) % RS] = make_float2(v.z, v.w);
+                }
+#pragma unroll
+                for (int u = 0; u < TI; u += 2) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xp + u);
+#pragma unroll
+                    for (int uu = 0; uu < 2; ++uu) {
+                        const float2 xr2 = uu ? make_float2(xv.z, xv.z) : make_float2(xv.x, xv.x);
+                        const float2 xi2 = uu ? make_float2(xv.w, xv.w) : make_float2(xv.y, xv.y);
+#pragma unroll
+                        for (int v = 0; v < TD; ++v) A1[v] = __ffma2_rn(xr2, W[(p * TI + u + uu + v) % RS], A1[v]);
+#pragma unroll
+                        for (int v = 0; v < TD; ++v) A2[v] = __ffma2_rn(xi2, W[(p * TI + u + uu + v) % RS], A2[v]);
+                    }
                 }
             }
         }
@@ -290,8 +348,11 @@ struct FirParams {
     int peek;
 };
 
-template <int TK, int TO, bool PACKED>
-__global__ void __launch_bounds__(512) fir_apply_kernel(const __grid_constant__ FirParams p) {
+// MODE 0: scalar FFMA; 1: FFMA2 with (t,t) pairs staged in shared memory; 2: FFMA2 with the pairs
+// built in registers (fewest shared-memory bytes per MAC, see slide_mac2n in lagstream.cuh)
+template <int TK, int TO, int MODE>
+__global__ void __launch_bounds__((TK * TO > 100) ? 256 : 512) fir_apply_kernel(const __grid_constant__ FirParams p) {
+    constexpr bool PACKED = (MODE == 1);
     extern __shared__ __align__(16) float2 smem[];
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
@@ -336,11 +397,12 @@ __global__ void __launch_bounds__(512) fir_apply_kernel(const __grid_constant__ 
     float2 acc[TO];
 #pragma unroll
     for (int v = 0; v < TO; ++v) acc[v] = make_float2(0.f, 0.f);
-    if (PACKED) {
+    if (MODE >= 1) {
         float2 A1[TO], A2[TO];
 #pragma unroll
         for (int v = 0; v < TO; ++v) { A1[v] = make_float2(0.f, 0.f); A2[v] = make_float2(0.f, 0.f); }
-        slide_mac2<TK, TO>(A1, A2, reinterpret_cast<const float4*>(tr), rs + tid * TO, p.Mpad / TK);
+        if (MODE == 1) slide_mac2<TK, TO>(A1, A2, reinterpret_cast<const float4*>(tr), rs + tid * TO, p.Mpad / TK);
+        else slide_mac2n<TK, TO>(A1, A2, tr, rs + tid * TO, p.Mpad / TK);
 #pragma unroll
         for (int v = 0; v < TO; ++v) acc[v] = make_float2(A1[v].x - A2[v].y, A1[v].y + A2[v].x);
     } else {
@@ -564,9 +626,15 @@ struct DopplerParams {
     int F;
     int logF;
     int R;
-    int nchunk;
+    int nchunk;              // partial rows reserved per Doppler block
     int HT;
+    int blk_len;             // stream layout (lagstream_kernel): rows actually written for block j =
+    long long per_cta;       //   stream_pieces(j, blk_len, per_cta); per_cta == 0: all nchunk rows
 };
+
+__device__ __forceinline__ int doppler_rows(const DopplerParams& p, int j) {
+    return p.per_cta > 0 ? stream_pieces(j, p.blk_len, p.per_cta) : p.nchunk;
+}
 
 // power-of-two F: radix-2 Stockham autosort in shared memory, CT range columns per CTA
 template <int CT>
@@ -583,7 +651,8 @@ __global__ void __launch_bounds__(256) doppler_fft_pow2_kernel(const __grid_cons
         float2 sum = make_float2(0.f, 0.f);
         if (k <= p.R) {
             const float2* src = p.partial + (size_t)j * p.nchunk * p.HT + (p.R - k);
-            for (int ch = 0; ch < p.nchunk; ++ch) {
+            const int rows = doppler_rows(p, j);
+            for (int ch = 0; ch < rows; ++ch) {
                 const float2 v = src[(size_t)ch * p.HT];
                 sum.x += v.x;
                 sum.y += v.y;
@@ -621,13 +690,14 @@ __global__ void __launch_bounds__(256) doppler_fft_pow2_kernel(const __grid_cons
 
 // any F: chunk-sum into a compact [F][R+1] buffer, then a direct DFT with an exact twiddle table
 __global__ void chunk_sum_kernel(const float2* __restrict__ partial, float2* __restrict__ P,
-                                 int F, int R, int nchunk, int HT) {
+                                 int F, int R, int nchunk, int HT, int blk_len, long long per_cta) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= F * (R + 1)) return;
     const int j = idx / (R + 1), k = idx - j * (R + 1);
     const float2* src = partial + (size_t)j * nchunk * HT + (R - k);
     float2 sum = make_float2(0.f, 0.f);
-    for (int ch = 0; ch < nchunk; ++ch) {
+    const int rows = per_cta > 0 ? stream_pieces(j, blk_len, per_cta) : nchunk;
+    for (int ch = 0; ch < rows; ++ch) {
         const float2 v = src[(size_t)ch * HT];
         sum.x += v.x;
         sum.y += v.y;

@@ -22,6 +22,7 @@
 
 #include "prcore.h"
 #include "kernels.cuh"
+#include "lagstream.cuh"
 #include "nlms.cuh"
 
 namespace {
@@ -30,8 +31,14 @@ using namespace prc;
 
 // slide_mac tile shapes: 10 x 10 complex MACs per step, lane stride
 // 10 complex = 80 B (odd multiple of 16 B => conflict-free 128-bit shared loads).
-constexpr int LC_TI = 10, LC_TD = 10;     // lagcorr: samples x lags per step
-constexpr int FIR_TK = 10, FIR_TO = 10;   // fir: taps x outputs per step
+constexpr int LC_TI = 10, LC_TD = 10;     // one-shot lagcorr kernel: samples x lags per step
+constexpr int FIR_TK = 10, FIR_TO = 10;   // legacy fir variants: taps x outputs per step
+// Register-tile variants of the pipelined kernels (PRC_TILE).  Shared-memory loads cost the FMA
+// pipe ~9 cycles per 128-bit load (scripts/microbench/fma_peak2.cu), and a TI x TD tile needs
+// 2*TI loads per TI*TD MACs, so a larger TD buys efficiency until registers run out.
+//   0: 10 x 10   1: 6 x 18   2: 14 x 14      (TD*8 B must be an odd multiple of 16 B)
+struct TileShape { int ti, td; };
+constexpr TileShape kTiles[3] = {{10, 10}, {6, 18}, {14, 14}};
 constexpr int FIR_THREADS = 128;
 constexpr size_t SMEM_LIMIT = 200 * 1024;
 
@@ -106,13 +113,13 @@ struct Ctx {
     bool own_stream = false;
     int nsm = 148;
     std::mutex mu;
-    DBuf ref, srv, out, clean, partial, win32, win64, dtaps32, dtaps64, lstaps, tw, pbuf, status,
+    DBuf refw, ref, srv, out, clean, partial, win32, win64, dtaps32, dtaps64, lstaps, tw, pbuf, status,
         nl_init, nl_taps;
     int tw_F = 0;
     std::vector<ProfRec> recs;
     void release() {
         cudaSetDevice(device);
-        for (DBuf* b : {&ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
+        for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
             b->release();
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -126,6 +133,8 @@ std::vector<Ctx*> g_all_ctx;
 std::atomic<bool> g_attrs_set[64];
 std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
 int g_tune_nchunk = -1, g_tune_g = -1;
+int g_tile = 0;          // measured on B200: 10x10 beats 6x18 / 14x14 (109 vs 117 / 115 us, profiles/r01_tuning.md)
+int g_stream = 1;          // persistent pipelined lag-correlation kernel (PRC_STREAM=0: one-shot kernel)
 int g_packed = 1;          // FFMA2 kernels (PRC_PACKED=0 selects the scalar-FFMA variant for A/B runs)
 std::once_flag g_env_once;
 
@@ -139,6 +148,8 @@ void read_env() {
     if (const char* e = getenv("PRC_TUNE_NCHUNK")) g_tune_nchunk = atoi(e);
     if (const char* e = getenv("PRC_TUNE_G")) g_tune_g = atoi(e);
     if (const char* e = getenv("PRC_PACKED")) g_packed = atoi(e);
+    if (const char* e = getenv("PRC_STREAM")) g_stream = atoi(e);
+    if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
 }
 
 int set_kernel_attrs(int device) {
@@ -146,8 +157,14 @@ int set_kernel_attrs(int device) {
     const int lim = (int)SMEM_LIMIT;
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(lagstream_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(lagstream_kernel<6, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(lagstream_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<FIR_TK, FIR_TO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<10, 10, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<6, 18, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fir_apply_kernel<14, 14, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(levinson_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(levinson_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(doppler_fft_pow2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -272,6 +289,52 @@ int choose_geo(int blk_len, long long outer, int nlag, int nsm, Geo* g) {
     return PRC_OK;
 }
 
+struct StreamGeo {
+    int H, HT, G, steps, threads, ncta, maxpieces;
+    long long per_cta, total;
+    size_t smem;
+};
+
+// CTAs per problem: fill every SM with two co-resident CTAs, but keep >= 2 full steps per CTA
+int choose_stream(int blk_len, int nblk, int nprob, int nlag, int nsm, StreamGeo* g) {
+    const int TI = kTiles[g_tile].ti, TD = kTiles[g_tile].td;
+    g->H = ceil_div(nlag, TD);
+    g->HT = g->H * TD;
+    if (g->H > 512) return fail(PRC_E_INVALID, "%d lags exceed the supported maximum of %d", nlag, 512 * TD);
+    const int max_threads = (TI * TD > 100) ? 256 : 512;     // the big tiles are compiled for <= 256 threads
+    if (g->H > max_threads) return fail(PRC_E_INVALID, "%d lags exceed the supported maximum of %d", nlag, max_threads * TD);
+    int G = std::max(1, std::min(32, 256 / g->H));
+    if (g_tune_g > 0) G = std::max(1, std::min(g_tune_g, max_threads / g->H));
+    g->total = (long long)nblk * blk_len;
+    long long want = std::max(1, 2 * nsm / nprob);
+    if (g_tune_nchunk > 0) want = g_tune_nchunk;
+    const long long min_per_cta = (long long)G * TI * 2;
+    want = std::min<long long>(want, std::max<long long>(1, g->total / min_per_cta));
+    g->per_cta = (g->total + want - 1) / want;
+    g->ncta = (int)((g->total + g->per_cta - 1) / g->per_cta);
+    g->G = (int)std::max<long long>(1, std::min<long long>(G, (g->per_cta + TI - 1) / TI));
+    g->steps = std::max(2, 100 / TI);
+    while (g->steps > 1 && (long long)g->G * g->steps * TI > g->per_cta + g->G * TI) --g->steps;
+    for (;;) {
+        const size_t Lmax = (size_t)g->G * g->steps * TI;
+        g->smem = (2 * (2 * Lmax + g->HT) + (size_t)g->G * g->HT) * sizeof(float2);
+        if (g->smem <= 100 * 1024 || g->steps == 1) break;
+        --g->steps;
+    }
+    if (g->smem > SMEM_LIMIT) return fail(PRC_E_INVALID, "lag-correlation tile needs %zu B of shared memory", g->smem);
+    g->maxpieces = (int)std::min<long long>(g->ncta, (blk_len + g->per_cta - 2) / g->per_cta + 1);
+    g->threads = ((g->H * g->G + 31) / 32) * 32;
+    return PRC_OK;
+}
+
+void launch_lagstream(dim3 grid, int threads, size_t smem, cudaStream_t st, const LagStreamParams& sp) {
+    switch (g_tile) {
+        case 0: lagstream_kernel<10, 10><<<grid, threads, smem, st>>>(sp); break;
+        case 1: lagstream_kernel<6, 18><<<grid, threads, smem, st>>>(sp); break;
+        default: lagstream_kernel<14, 14><<<grid, threads, smem, st>>>(sp); break;
+    }
+}
+
 // --------------------------------------------------------------------------- device pipelines
 // All pointers are device pointers; everything is enqueued on c->stream.
 
@@ -303,7 +366,45 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
         taps = dtaps32;
     }
     if (ntaps > (1ll << 30)) return fail(PRC_E_INVALID, "decimator too long");
-    Geo g;
+    Geo g{};
+    long long d_per_cta = 0;
+    if (g_stream && taps == nullptr && ntaps >= 64) {   // tiny Doppler blocks: one flush per block would dominate
+        StreamGeo sg;
+        TRY(choose_stream((int)ntaps, F, 1, R + 1, c->nsm, &sg));
+        TRY(c->partial.ensure((size_t)F * sg.maxpieces * sg.HT * sizeof(float2)));
+        const float2* xw = ref;
+        if (win32) {
+            TRY(c->refw.ensure((size_t)n * sizeof(float2)));
+            {
+                ProfScope ps(c, K_MISC);
+                weight_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(ref, win32, c->refw.as<float2>(), (int)n);
+            }
+            TRY(check_launch("weight_kernel"));
+            xw = c->refw.as<float2>();
+        }
+        LagStreamParams sp{};
+        sp.x = xw;
+        sp.s[0] = srv; sp.s[1] = srv;
+        sp.dmin[0] = 0; sp.dmin[1] = 0;
+        sp.n = (int)n;
+        sp.blk_first_lo = (long long)c0 - (ntaps - 1);
+        sp.blk_stride = D;
+        sp.blk_len = (int)ntaps;
+        sp.nblk = F;
+        sp.total = sg.total;
+        sp.per_cta = sg.per_cta;
+        sp.H = sg.H; sp.G = sg.G; sp.steps = sg.steps;
+        sp.maxpieces = sg.maxpieces;
+        sp.partial = c->partial.as<float2>();
+        {
+            ProfScope ps(c, K_LAGCORR_CAF);
+            launch_lagstream(dim3(sg.ncta, 1), sg.threads, sg.smem, c->stream, sp);
+        }
+        TRY(check_launch("lagstream_kernel(caf)"));
+        g.nchunk = sg.maxpieces;
+        g.HT = sg.HT;
+        d_per_cta = sg.per_cta;
+    } else {
     TRY(choose_geo((int)ntaps, F, R + 1, c->nsm, &g));
     TRY(c->partial.ensure((size_t)F * g.nchunk * g.HT * sizeof(float2)));
 
@@ -329,6 +430,7 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
         else lagcorr_kernel<LC_TI, LC_TD, false><<<grid, g.threads, g.smem, c->stream>>>(p);
     }
     TRY(check_launch("lagcorr_kernel(caf)"));
+    }
 
     // Doppler stage
     if (c->tw_F != F) {
@@ -342,6 +444,7 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     d.tw = c->tw.as<float2>();
     d.out = out;
     d.F = F; d.R = R; d.nchunk = g.nchunk; d.HT = g.HT;
+    d.blk_len = (int)ntaps; d.per_cta = d_per_cta;
     int logF = 0;
     while ((1 << logF) < F) ++logF;
     d.logF = logF;
@@ -362,7 +465,7 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     } else {
         TRY(c->pbuf.ensure((size_t)F * (R + 1) * sizeof(float2)));
         chunk_sum_kernel<<<ceil_div((long long)F * (R + 1), 256), 256, 0, c->stream>>>(
-            c->partial.as<float2>(), c->pbuf.as<float2>(), F, R, g.nchunk, g.HT);
+            c->partial.as<float2>(), c->pbuf.as<float2>(), F, R, g.nchunk, g.HT, (int)ntaps, d_per_cta);
         TRY(check_launch("chunk_sum_kernel"));
         doppler_dft_kernel<<<dim3(ceil_div(R + 1, 128), F), 128, 0, c->stream>>>(
             c->pbuf.as<float2>(), c->tw.as<float2>(), out, F, R);
@@ -378,11 +481,37 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
     const int M = filter_len + peek;
     if (M > 2048) return fail(PRC_E_INVALID, "%d taps exceed the Toeplitz solver's maximum of 2048", M);
-    Geo g;
-    TRY(choose_geo((int)n, 2, M, c->nsm, &g));
-    TRY(c->partial.ensure((size_t)2 * g.nchunk * g.HT * sizeof(float2)));
+    Geo g{};
     TRY(c->lstaps.ensure((size_t)M * sizeof(float2)));
     TRY(c->status.ensure(sizeof(int)));
+    if (g_stream) {
+        StreamGeo sg;
+        TRY(choose_stream((int)n, 1, 2, M, c->nsm, &sg));
+        TRY(c->partial.ensure((size_t)2 * sg.maxpieces * sg.HT * sizeof(float2)));
+        LagStreamParams sp{};
+        sp.x = ref;
+        sp.s[0] = ref; sp.s[1] = srv;
+        sp.dmin[0] = 0; sp.dmin[1] = -peek;
+        sp.n = (int)n;
+        sp.blk_first_lo = 0;
+        sp.blk_stride = 0;
+        sp.blk_len = (int)n;
+        sp.nblk = 1;
+        sp.total = sg.total;
+        sp.per_cta = sg.per_cta;
+        sp.H = sg.H; sp.G = sg.G; sp.steps = sg.steps;
+        sp.maxpieces = sg.maxpieces;
+        sp.partial = c->partial.as<float2>();
+        {
+            ProfScope ps(c, K_LAGCORR_LS);
+            launch_lagstream(dim3(sg.ncta, 2), sg.threads, sg.smem, c->stream, sp);
+        }
+        TRY(check_launch("lagstream_kernel(ls)"));
+        g.nchunk = sg.maxpieces;      // == pieces of the single block == ncta
+        g.HT = sg.HT;
+    } else {
+    TRY(choose_geo((int)n, 2, M, c->nsm, &g));
+    TRY(c->partial.ensure((size_t)2 * g.nchunk * g.HT * sizeof(float2)));
 
     LagCorrParams p{};
     p.x = ref;
@@ -404,6 +533,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         else lagcorr_kernel<LC_TI, LC_TD, false><<<dim3(g.nchunk, 2), g.threads, g.smem, c->stream>>>(p);
     }
     TRY(check_launch("lagcorr_kernel(ls)"));
+    }
 
     LevinsonParams lp{};
     lp.partial = c->partial.as<float2>();
@@ -423,14 +553,21 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     FirParams fp{};
     fp.ref = ref; fp.srv = srv; fp.taps = c->lstaps.as<float2>(); fp.out = out;
     fp.n = (int)n; fp.M = M; fp.peek = peek;
-    fp.Mpad = ceil_div(M, FIR_TK) * FIR_TK;
-    const int LO = FIR_THREADS * FIR_TO;
-    const size_t sm = (size_t)((g_packed ? 2 : 1) * fp.Mpad + LO + fp.Mpad) * sizeof(float2);
+    const int mode = g_stream ? 2 : (g_packed ? 1 : 0);
+    const int tk = mode == 2 ? kTiles[g_tile].ti : FIR_TK, to = mode == 2 ? kTiles[g_tile].td : FIR_TO;
+    fp.Mpad = ceil_div(M, tk) * tk;
+    if (fp.Mpad & 1) fp.Mpad += tk;          // keep the ref window 16-byte aligned behind the taps
+    const int LO = FIR_THREADS * to;
+    const size_t sm = (size_t)((mode == 1 ? 2 : 1) * fp.Mpad + LO + fp.Mpad) * sizeof(float2);
     if (sm > SMEM_LIMIT) return fail(PRC_E_INVALID, "%d taps exceed the FIR kernel's shared memory", M);
     {
         ProfScope ps(c, K_FIR);
-        if (g_packed) fir_apply_kernel<FIR_TK, FIR_TO, true><<<ceil_div(n, LO), FIR_THREADS, sm, c->stream>>>(fp);
-        else fir_apply_kernel<FIR_TK, FIR_TO, false><<<ceil_div(n, LO), FIR_THREADS, sm, c->stream>>>(fp);
+        const int grid = ceil_div(n, LO);
+        if (mode == 0) fir_apply_kernel<FIR_TK, FIR_TO, 0><<<grid, FIR_THREADS, sm, c->stream>>>(fp);
+        else if (mode == 1) fir_apply_kernel<FIR_TK, FIR_TO, 1><<<grid, FIR_THREADS, sm, c->stream>>>(fp);
+        else if (g_tile == 0) fir_apply_kernel<10, 10, 2><<<grid, FIR_THREADS, sm, c->stream>>>(fp);
+        else if (g_tile == 1) fir_apply_kernel<6, 18, 2><<<grid, FIR_THREADS, sm, c->stream>>>(fp);
+        else fir_apply_kernel<14, 14, 2><<<grid, FIR_THREADS, sm, c->stream>>>(fp);
     }
     TRY(check_launch("fir_apply_kernel"));
     if (taps_out)
