@@ -451,10 +451,10 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     const bool pow2 = (1 << logF) == F && F >= 2;
     ProfScope ps_doppler(c, K_DOPPLER);
     if (pow2 && F <= 8192) {
-        if (F <= 1024) {
+        if (F <= 1024 && ceil_div(R + 1, 8) >= c->nsm) {
             const size_t sm = (size_t)2 * F * 8 * sizeof(float2);
             doppler_fft_pow2_kernel<8><<<ceil_div(R + 1, 8), 256, sm, c->stream>>>(d);
-        } else if (F <= 4096) {
+        } else if (F <= 4096) {     // also the small-grid case: 2 columns per CTA fill more SMs
             const size_t sm = (size_t)2 * F * 2 * sizeof(float2);
             doppler_fft_pow2_kernel<2><<<ceil_div(R + 1, 2), 256, sm, c->stream>>>(d);
         } else {

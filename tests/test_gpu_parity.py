@@ -250,3 +250,32 @@ def test_nlms_short_input_is_all_zero():
     ref, srv = synth.make_frame(30, "P0")
     out = prb.NLMS_filter(ref, srv, 25, 0.05, 10)
     assert out.shape == (30,) and not out.any()
+
+
+# ------------------------------------------------------------------ BASELINE config 4 (2M samples, NLMS)
+def test_nlms_config4_matches_c_oracle():
+    """2**21-sample CPI, filterLen = 400 (+10 peek): the Python reference needs ~18 s for this, the
+    plain-C oracle (pinned to the reference by tests/test_oracle_golden.py) a few seconds."""
+    from oracle import clutter_oracle as co
+    n, fl = 2 ** 21, 400
+    ref, srv = synth.make_frame(n, "P1", frame=4)
+    want, ww = co.block_nlms_oracle_c(ref, srv, fl, 0.05, 10, 1)
+    got, gw = prb.NLMS_filter(ref, srv, fl, 0.05, 10, None, True)
+    assert G.rel_inf(got, want) <= TOL
+    assert G.rel_inf(gw, ww) <= 5e-5
+    assert not got[:fl].any() and not got[-10:].any()
+    wantb, wwb = co.block_nlms_oracle_c(ref, srv, fl, 0.05, 10, 64)
+    gotb, gwb = prb.block_NLMS(ref, srv, fl, 0.05, 10, 64, None, True)
+    assert G.rel_inf(gotb, wantb) <= TOL
+    assert G.rel_inf(gwb, wwb) <= 5e-5
+
+
+def test_xambg_config4_grid_matches_oracle():
+    from oracle import xambg_oracle as xo
+    n, F, R = 2 ** 21, 512, 400
+    ref, srv = synth.make_frame(n, "P1", frame=4)
+    w = signal.get_window(("kaiser", 5.0), n)
+    # oracle on a subset of lags keeps the CPU time at a few seconds; columns are independent
+    want = xo.fast_xambg_oracle(ref, srv, 40, F, n, w)          # lags 0..40 -> columns R-40..R
+    got = prb.fast_xambg(ref, srv, R, F, n, w)
+    assert G.rel_inf(got[:, R - 40:, :], want) <= TOL
