@@ -23,6 +23,7 @@
 #include "prcore.h"
 #include "kernels.cuh"
 #include "lagstream.cuh"
+#include "toepcorr.cuh"
 #include "nlms.cuh"
 
 namespace {
@@ -113,12 +114,14 @@ struct Ctx {
     bool own_stream = false;
     int nsm = 148;
     std::mutex mu;
+    DBuf tcplane[9];          // bf16 planes of the tensor-core path: x[3], s0[3], s1[3]
     DBuf refw, ref, srv, out, clean, partial, win32, win64, dtaps32, dtaps64, lstaps, tw, pbuf, status,
         nl_init, nl_taps;
     int tw_F = 0;
     std::vector<ProfRec> recs;
     void release() {
         cudaSetDevice(device);
+        for (DBuf& b : tcplane) b.release();
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
             b->release();
@@ -134,6 +137,7 @@ std::atomic<bool> g_attrs_set[64];
 std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
 int g_tune_nchunk = -1, g_tune_g = -1;
 int g_tile = 0;          // measured on B200: 10x10 beats 6x18 / 14x14 (109 vs 117 / 115 us, profiles/r01_tuning.md)
+int g_tc = 1;              // tcgen05 Toeplitz-GEMM for the LS correlations (PRC_TC=0: FP32 lagstream kernel)
 int g_stream = 1;          // persistent pipelined lag-correlation kernel (PRC_STREAM=0: one-shot kernel)
 int g_packed = 1;          // FFMA2 kernels (PRC_PACKED=0 selects the scalar-FFMA variant for A/B runs)
 std::once_flag g_env_once;
@@ -149,6 +153,7 @@ void read_env() {
     if (const char* e = getenv("PRC_TUNE_G")) g_tune_g = atoi(e);
     if (const char* e = getenv("PRC_PACKED")) g_packed = atoi(e);
     if (const char* e = getenv("PRC_STREAM")) g_stream = atoi(e);
+    if (const char* e = getenv("PRC_TC")) g_tc = atoi(e);
     if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
 }
 
@@ -157,6 +162,7 @@ int set_kernel_attrs(int device) {
     const int lim = (int)SMEM_LIMIT;
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::toepcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<6, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -484,7 +490,48 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     Geo g{};
     TRY(c->lstaps.ensure((size_t)M * sizeof(float2)));
     TRY(c->status.ensure(sizeof(int)));
-    if (g_stream) {
+    const int tc_npass = ceil_div(2 * (64 + M), tc::NPASS);
+    const int tc_ranges = c->nsm / (2 * tc_npass);
+    const int tc_nk = ceil_div(n, 1024);
+    const int tc_ht = ceil_div(M, 2) * 2;
+    if (g_tc && tc_ranges >= 1 && tc_nk >= 2 * tc_ranges && tc::toep_smem_bytes(tc_ht) <= SMEM_LIMIT) {
+        // ---- tensor-core path: BF16x3 Toeplitz GEMM (toepcorr.cuh)
+        const long long nx = (long long)tc_nk * 1024;
+        const long long slen = nx + (long long)tc_npass * 128;
+        const bool alias_x = (nx == n);              // x (zero tail) and s0 (circular tail) only differ beyond n
+        for (int k = 0; k < 9; ++k) {
+            if (k < 3 && alias_x) continue;
+            TRY(c->tcplane[k].ensure((size_t)(k < 3 ? nx : slen) * 2 * sizeof(uint16_t)));
+        }
+        TRY(c->partial.ensure((size_t)2 * tc_npass * tc_ranges * tc_ht * sizeof(float2)));
+        {
+            ProfScope ps(c, K_MISC);
+            if (!alias_x)
+                tc::bf16_split_kernel<<<ceil_div(nx, 256), 256, 0, c->stream>>>(
+                    ref, (int)n, 0, c->tcplane[0].as<uint16_t>(), c->tcplane[1].as<uint16_t>(), c->tcplane[2].as<uint16_t>(), nx, n);
+            tc::bf16_split_kernel<<<ceil_div(slen, 256), 256, 0, c->stream>>>(
+                ref, (int)n, 0, c->tcplane[3].as<uint16_t>(), c->tcplane[4].as<uint16_t>(), c->tcplane[5].as<uint16_t>(), slen, slen);
+            tc::bf16_split_kernel<<<ceil_div(slen, 256), 256, 0, c->stream>>>(
+                srv, (int)n, -peek, c->tcplane[6].as<uint16_t>(), c->tcplane[7].as<uint16_t>(), c->tcplane[8].as<uint16_t>(), slen, slen);
+        }
+        TRY(check_launch("bf16_split_kernel"));
+        tc::ToepParams tp{};
+        for (int k = 0; k < 3; ++k) {
+            tp.x[k] = c->tcplane[alias_x ? 3 + k : k].as<uint16_t>();
+            tp.s[0][k] = c->tcplane[3 + k].as<uint16_t>();
+            tp.s[1][k] = c->tcplane[6 + k].as<uint16_t>();
+        }
+        tp.nk = tc_nk; tp.nlag = M; tp.npass = tc_npass; tp.ranges = tc_ranges; tp.HT = tc_ht;
+        tp.partial = c->partial.as<float2>();
+        tp.debug_tile = nullptr; tp.debug_clk = nullptr;
+        {
+            ProfScope ps(c, K_LAGCORR_LS);
+            tc::toepcorr_kernel<<<2 * tc_npass * tc_ranges, tc::THREADS, tc::toep_smem_bytes(tc_ht), c->stream>>>(tp);
+        }
+        TRY(check_launch("toepcorr_kernel"));
+        g.nchunk = tc_npass * tc_ranges;
+        g.HT = tc_ht;
+    } else if (g_stream) {
         StreamGeo sg;
         TRY(choose_stream((int)n, 1, 2, M, c->nsm, &sg));
         TRY(c->partial.ensure((size_t)2 * sg.maxpieces * sg.HT * sizeof(float2)));
