@@ -552,27 +552,53 @@ __global__ void __launch_bounds__(E == 1 ? 1024 : 512) levinson_kernel(const __g
         const double2 d = pivot[buf * 2 + 1];
         const double den = 1.0 - (ef.x * ef.x + ef.y * ef.y);
         if (!(den > 0.0) || !isfinite(den)) bad = 1;
-        const double al = 1.0 / den;
+        // The recursion is a chain of dependent fp64 operations (~40 cycles each on this part), so
+        // everything that does not need 1/den is computed while the reciprocal is in flight, and the
+        // reciprocal itself is a float seed + two Newton steps instead of the IEEE division routine.
+        double al;
+        {
+            const double y0 = (double)__frcp_rn((float)den);
+            const double e0 = fma(-den, y0, 1.0);
+            const double y1 = fma(y0, e0, y0);
+            const double e1 = fma(-den, y1, 1.0);
+            al = fma(y1, e1, y1);
+            if (!isfinite(al)) bad = 1;
+        }
         double2 nQ[E], nb[E];
+        // Only half of the state matters at step n: (f, b, x) live on elements j <= n, (P, Q, rho) on
+        // j >= n.  Threads are ordered by j, so at most one warp diverges.
+        // warp-uniform guards: a warp whose elements are all below / above n skips the other half
+        // entirely (per-thread conditions alone are turned into predication and save nothing)
+        const int wlo = (tid & ~31) * E, whi = wlo + 32 * E - 1;
+        const bool warp_has_P = whi >= n, warp_has_F = wlo <= n;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = tid * E + e;
-            const double2 q0 = (j == 0) ? make_double2(ef.x, -ef.y) : Qs[e];
-            const double2 a = zmul(ef, q0);           // ef * Qs
-            const double2 b = zmulc(P[e], ef);        // conj(ef) * P
-            const double2 np = make_double2(al * (P[e].x - a.x), al * (P[e].y - a.y));
-            nQ[e] = make_double2(al * (q0.x - b.x), al * (q0.y - b.y));
-            const double2 c = zmul(ef, bs[e]);
-            const double2 g = zmulc(f[e], ef);        // conj(ef) * f
-            const double2 nf = make_double2(al * (f[e].x - c.x), al * (f[e].y - c.y));
-            nb[e] = make_double2(al * (bs[e].x - g.x), al * (bs[e].y - g.y));
-            const double2 dx = zmul(d, nb[e]);
-            x[e] = make_double2(x[e].x + dx.x, x[e].y + dx.y);
-            const double2 dq = zmul(d, nQ[e]);
-            rho[e] = make_double2(rho[e].x - dq.x, rho[e].y - dq.y);
-            P[e] = np;
-            f[e] = nf;
-            if (j == n + 1) { pivot[(buf ^ 1) * 2 + 0] = np; pivot[(buf ^ 1) * 2 + 1] = rho[e]; }
+            nQ[e] = make_double2(0.0, 0.0);
+            nb[e] = make_double2(0.0, 0.0);
+            if (warp_has_P && j >= n) {
+                const double2 q0 = (j == 0) ? make_double2(ef.x, -ef.y) : Qs[e];
+                const double2 a = zmul(ef, q0);
+                const double2 b = zmulc(P[e], ef);        // conj(ef) * P
+                const double2 tp = make_double2(P[e].x - a.x, P[e].y - a.y);      // P' / al
+                const double2 tq = make_double2(q0.x - b.x, q0.y - b.y);          // Q' / al
+                const double2 dq = zmul(d, tq);                                   // d * Q' / al
+                const double2 np = make_double2(al * tp.x, al * tp.y);
+                nQ[e] = make_double2(al * tq.x, al * tq.y);
+                rho[e] = make_double2(fma(-al, dq.x, rho[e].x), fma(-al, dq.y, rho[e].y));
+                P[e] = np;
+                if (j == n + 1) { pivot[(buf ^ 1) * 2 + 0] = np; pivot[(buf ^ 1) * 2 + 1] = rho[e]; }
+            }
+            if (warp_has_F && j <= n) {
+                const double2 c = zmul(ef, bs[e]);
+                const double2 g = zmulc(f[e], ef);        // conj(ef) * f
+                const double2 tf = make_double2(f[e].x - c.x, f[e].y - c.y);
+                const double2 tb = make_double2(bs[e].x - g.x, bs[e].y - g.y);
+                const double2 dx = zmul(d, tb);
+                nb[e] = make_double2(al * tb.x, al * tb.y);
+                x[e] = make_double2(fma(al, dx.x, x[e].x), fma(al, dx.y, x[e].y));
+                f[e] = make_double2(al * tf.x, al * tf.y);
+            }
         }
         // shift by one element: (Qs, bs)[j] <- (nQ, nb)[j-1]
         double2 inQ, inB;
@@ -630,7 +656,21 @@ struct DopplerParams {
     int HT;
     int blk_len;             // stream layout (lagstream_kernel): rows actually written for block j =
     long long per_cta;       //   stream_pieces(j, blk_len, per_cta); per_cta == 0: all nchunk rows
+    // optional boundary sample of every Doppler block (tensor-core CAF: the GEMM covers D of the D+1
+    // samples of a block, the last one, i = j*bstride + boff, is added here)
+    const float2* bx;
+    const float2* bs;
+    long long bstride, boff;
+    int n;
 };
+
+__device__ __forceinline__ float2 doppler_boundary(const DopplerParams& p, int j, int k) {
+    const long long i = (long long)j * p.bstride + p.boff;
+    if (p.bx == nullptr || i < 0 || i >= p.n) return make_float2(0.f, 0.f);
+    const float2 xv = p.bx[i];
+    const float2 sv = p.bs[(i + (p.R - k)) % p.n];
+    return make_float2(xv.x * sv.x + xv.y * sv.y, xv.y * sv.x - xv.x * sv.y);      // x * conj(s)
+}
 
 __device__ __forceinline__ int doppler_rows(const DopplerParams& p, int j) {
     return p.per_cta > 0 ? stream_pieces(j, p.blk_len, p.per_cta) : p.nchunk;
@@ -657,6 +697,9 @@ __global__ void __launch_bounds__(256) doppler_fft_pow2_kernel(const __grid_cons
                 sum.x += v.x;
                 sum.y += v.y;
             }
+            const float2 bv = doppler_boundary(p, j, k);
+            sum.x += bv.x;
+            sum.y += bv.y;
         }
         a[idx] = sum;
     }
@@ -690,7 +733,8 @@ __global__ void __launch_bounds__(256) doppler_fft_pow2_kernel(const __grid_cons
 
 // any F: chunk-sum into a compact [F][R+1] buffer, then a direct DFT with an exact twiddle table
 __global__ void chunk_sum_kernel(const float2* __restrict__ partial, float2* __restrict__ P,
-                                 int F, int R, int nchunk, int HT, int blk_len, long long per_cta) {
+                                 int F, int R, int nchunk, int HT, int blk_len, long long per_cta,
+                                 const __grid_constant__ DopplerParams bp) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= F * (R + 1)) return;
     const int j = idx / (R + 1), k = idx - j * (R + 1);
@@ -702,7 +746,8 @@ __global__ void chunk_sum_kernel(const float2* __restrict__ partial, float2* __r
         sum.x += v.x;
         sum.y += v.y;
     }
-    P[idx] = sum;
+    const float2 bv = doppler_boundary(bp, j, k);
+    P[idx] = make_float2(sum.x + bv.x, sum.y + bv.y);
 }
 
 __global__ void doppler_dft_kernel(const float2* __restrict__ P, const float2* __restrict__ tw,

@@ -137,6 +137,7 @@ std::atomic<bool> g_attrs_set[64];
 std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
 int g_tune_nchunk = -1, g_tune_g = -1;
 int g_tile = 0;          // measured on B200: 10x10 beats 6x18 / 14x14 (109 vs 117 / 115 us, profiles/r01_tuning.md)
+int g_tc_caf = 1;          // tensor-core path for the CAF block sums as well (PRC_TC_CAF=0: FP32 lagstream)
 int g_tc = 1;              // tcgen05 Toeplitz-GEMM for the LS correlations (PRC_TC=0: FP32 lagstream kernel)
 int g_stream = 1;          // persistent pipelined lag-correlation kernel (PRC_STREAM=0: one-shot kernel)
 int g_packed = 1;          // FFMA2 kernels (PRC_PACKED=0 selects the scalar-FFMA variant for A/B runs)
@@ -154,6 +155,7 @@ void read_env() {
     if (const char* e = getenv("PRC_PACKED")) g_packed = atoi(e);
     if (const char* e = getenv("PRC_STREAM")) g_stream = atoi(e);
     if (const char* e = getenv("PRC_TC")) g_tc = atoi(e);
+    if (const char* e = getenv("PRC_TC_CAF")) g_tc_caf = atoi(e);
     if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
 }
 
@@ -162,7 +164,8 @@ int set_kernel_attrs(int device) {
     const int lim = (int)SMEM_LIMIT;
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CU(cudaFuncSetAttribute(tc::toepcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<6, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -352,7 +355,8 @@ int decimator_offset(long long ntaps, long long D) {   // resample_poly alignmen
 }
 
 int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int R, int F,
-                 const float* win32, const float* dtaps32, long long ndtaps, float2* out) {
+                 const float* win32, const float* dtaps32, long long ndtaps, float2* out,
+                 bool refw_ready = false) {
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
     if (F < 1 || R < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", F, R);
     const long long D = n / F;
@@ -374,12 +378,75 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     if (ntaps > (1ll << 30)) return fail(PRC_E_INVALID, "decimator too long");
     Geo g{};
     long long d_per_cta = 0;
-    if (g_stream && taps == nullptr && ntaps >= 64) {   // tiny Doppler blocks: one flush per block would dominate
+    const float2* bnd_x = nullptr;                  // boundary-sample correction of the tensor-core path
+    const int caf_npass = ceil_div(2 * (64 + R + 1), tc::NPASS);
+    const int caf_ht = ceil_div(R + 1, 2) * 2;
+    if (g_tc && g_tc_caf && taps == nullptr && D >= 1024 && D % 1024 == 0 && ntaps == D + 1 && c0 == D / 2 &&
+        (long long)F * caf_npass >= c->nsm && tc::toep_smem_bytes(caf_ht) <= SMEM_LIMIT) {
+        // ---- tensor-core CAF: one (Doppler block, pass) item per accumulation, persistent CTAs
+        const float2* xw = ref;
+        if (win32 && refw_ready) {
+            xw = c->refw.as<float2>();
+        } else if (win32) {
+            TRY(c->refw.ensure((size_t)n * sizeof(float2)));
+            {
+                ProfScope ps(c, K_MISC);
+                weight_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(ref, win32, c->refw.as<float2>(), (int)n);
+            }
+            TRY(check_launch("weight_kernel"));
+            xw = c->refw.as<float2>();
+        }
+        const long long nx = (long long)F * D;
+        const long long slen = nx + (long long)caf_npass * 128;
+        for (int k = 0; k < 6; ++k) TRY(c->tcplane[k].ensure((size_t)(k < 3 ? nx : slen) * 2 * sizeof(uint16_t)));
+        TRY(c->partial.ensure((size_t)F * caf_npass * caf_ht * sizeof(float2)));
+        tc::PrepParams pp{};
+        pp.sig[0] = xw; pp.sig[1] = srv;
+        pp.dmin[0] = -(int)(D / 2); pp.dmin[1] = -(int)(D / 2);
+        pp.zero_outside[0] = 1; pp.zero_outside[1] = 0;
+        for (int k = 0; k < 3; ++k) { pp.plane[0][k] = c->tcplane[k].as<uint16_t>(); pp.plane[1][k] = c->tcplane[3 + k].as<uint16_t>(); }
+        pp.win = nullptr; pp.refw = nullptr;
+        pp.n = (int)n;
+        pp.len = slen;                       // the x planes are only read below nx; both are sized >= what is written
+        // x planes hold nx samples: run the x signal with its own length
+        {
+            ProfScope ps(c, K_MISC);
+            tc::PrepParams px = pp;
+            px.len = nx;
+            px.sig[1] = xw; px.plane[1][0] = pp.plane[0][0]; px.plane[1][1] = pp.plane[0][1]; px.plane[1][2] = pp.plane[0][2];
+            tc::tc_prep_kernel<<<dim3(ceil_div(nx, 1024), 1), 256, 0, c->stream>>>(px);
+            tc::PrepParams py = pp;
+            py.sig[0] = srv; py.zero_outside[0] = 0;
+            for (int k = 0; k < 3; ++k) py.plane[0][k] = pp.plane[1][k];
+            tc::tc_prep_kernel<<<dim3(ceil_div(slen, 1024), 1), 256, 0, c->stream>>>(py);
+        }
+        TRY(check_launch("tc_prep_kernel(caf)"));
+        tc::ToepParams tp{};
+        for (int k = 0; k < 3; ++k) {
+            tp.x[k] = c->tcplane[k].as<uint16_t>();
+            tp.s[0][k] = c->tcplane[3 + k].as<uint16_t>();
+            tp.s[1][k] = c->tcplane[3 + k].as<uint16_t>();
+        }
+        tp.nk = (int)(nx / 1024); tp.nlag = R + 1; tp.npass = caf_npass; tp.ranges = 0;
+        tp.kb = (int)(D / 1024); tp.nblk = F; tp.HT = caf_ht;
+        tp.partial = c->partial.as<float2>();
+        tp.debug_tile = nullptr; tp.debug_clk = nullptr;
+        {
+            ProfScope ps(c, K_LAGCORR_CAF);
+            tc::toepcorr_kernel<false><<<c->nsm, tc::THREADS, tc::toep_smem_bytes(caf_ht), c->stream>>>(tp);
+        }
+        TRY(check_launch("toepcorr_kernel(caf)"));
+        g.nchunk = caf_npass;
+        g.HT = caf_ht;
+        bnd_x = xw;
+    } else if (g_stream && taps == nullptr && ntaps >= 64) {   // tiny Doppler blocks: one flush per block would dominate
         StreamGeo sg;
         TRY(choose_stream((int)ntaps, F, 1, R + 1, c->nsm, &sg));
         TRY(c->partial.ensure((size_t)F * sg.maxpieces * sg.HT * sizeof(float2)));
         const float2* xw = ref;
-        if (win32) {
+        if (win32 && refw_ready) {
+            xw = c->refw.as<float2>();           // ref * window already written by the LS stage's prep kernel
+        } else if (win32) {
             TRY(c->refw.ensure((size_t)n * sizeof(float2)));
             {
                 ProfScope ps(c, K_MISC);
@@ -451,6 +518,7 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     d.out = out;
     d.F = F; d.R = R; d.nchunk = g.nchunk; d.HT = g.HT;
     d.blk_len = (int)ntaps; d.per_cta = d_per_cta;
+    d.bx = bnd_x; d.bs = srv; d.bstride = D; d.boff = c0; d.n = (int)n;
     int logF = 0;
     while ((1 << logF) < F) ++logF;
     d.logF = logF;
@@ -471,7 +539,7 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     } else {
         TRY(c->pbuf.ensure((size_t)F * (R + 1) * sizeof(float2)));
         chunk_sum_kernel<<<ceil_div((long long)F * (R + 1), 256), 256, 0, c->stream>>>(
-            c->partial.as<float2>(), c->pbuf.as<float2>(), F, R, g.nchunk, g.HT, (int)ntaps, d_per_cta);
+            c->partial.as<float2>(), c->pbuf.as<float2>(), F, R, g.nchunk, g.HT, (int)ntaps, d_per_cta, d);
         TRY(check_launch("chunk_sum_kernel"));
         doppler_dft_kernel<<<dim3(ceil_div(R + 1, 128), F), 128, 0, c->stream>>>(
             c->pbuf.as<float2>(), c->tw.as<float2>(), out, F, R);
@@ -481,7 +549,8 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
 }
 
 int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek,
-              double reg, float2* out, float2* taps_out) {
+              double reg, float2* out, float2* taps_out, const float* win32 = nullptr, bool* refw_ready = nullptr) {
+    if (refw_ready) *refw_ready = false;
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
     if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
         return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
@@ -504,17 +573,25 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
             TRY(c->tcplane[k].ensure((size_t)(k < 3 ? nx : slen) * 2 * sizeof(uint16_t)));
         }
         TRY(c->partial.ensure((size_t)2 * tc_npass * tc_ranges * tc_ht * sizeof(float2)));
+        const bool fold = win32 != nullptr && refw_ready != nullptr;
+        if (fold) TRY(c->refw.ensure((size_t)n * sizeof(float2)));
         {
             ProfScope ps(c, K_MISC);
             if (!alias_x)
                 tc::bf16_split_kernel<<<ceil_div(nx, 256), 256, 0, c->stream>>>(
                     ref, (int)n, 0, c->tcplane[0].as<uint16_t>(), c->tcplane[1].as<uint16_t>(), c->tcplane[2].as<uint16_t>(), nx, n);
-            tc::bf16_split_kernel<<<ceil_div(slen, 256), 256, 0, c->stream>>>(
-                ref, (int)n, 0, c->tcplane[3].as<uint16_t>(), c->tcplane[4].as<uint16_t>(), c->tcplane[5].as<uint16_t>(), slen, slen);
-            tc::bf16_split_kernel<<<ceil_div(slen, 256), 256, 0, c->stream>>>(
-                srv, (int)n, -peek, c->tcplane[6].as<uint16_t>(), c->tcplane[7].as<uint16_t>(), c->tcplane[8].as<uint16_t>(), slen, slen);
+            tc::PrepParams pp{};
+            pp.sig[0] = ref; pp.sig[1] = srv;
+            pp.dmin[0] = 0; pp.dmin[1] = -peek;
+            for (int k = 0; k < 3; ++k) { pp.plane[0][k] = c->tcplane[3 + k].as<uint16_t>(); pp.plane[1][k] = c->tcplane[6 + k].as<uint16_t>(); }
+            pp.win = fold ? win32 : nullptr;
+            pp.refw = fold ? c->refw.as<float2>() : nullptr;
+            pp.n = (int)n;
+            pp.len = slen;
+            tc::tc_prep_kernel<<<dim3(ceil_div(slen, 1024), 2), 256, 0, c->stream>>>(pp);
         }
-        TRY(check_launch("bf16_split_kernel"));
+        TRY(check_launch("tc_prep_kernel"));
+        if (fold) *refw_ready = true;
         tc::ToepParams tp{};
         for (int k = 0; k < 3; ++k) {
             tp.x[k] = c->tcplane[alias_x ? 3 + k : k].as<uint16_t>();
@@ -526,7 +603,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         tp.debug_tile = nullptr; tp.debug_clk = nullptr;
         {
             ProfScope ps(c, K_LAGCORR_LS);
-            tc::toepcorr_kernel<<<2 * tc_npass * tc_ranges, tc::THREADS, tc::toep_smem_bytes(tc_ht), c->stream>>>(tp);
+            tc::toepcorr_kernel<true><<<2 * tc_npass * tc_ranges, tc::THREADS, tc::toep_smem_bytes(tc_ht), c->stream>>>(tp);
         }
         TRY(check_launch("toepcorr_kernel"));
         g.nchunk = tc_npass * tc_ranges;
@@ -951,8 +1028,9 @@ int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_
     }
     const float* win32;
     TRY(stage_window(c, window, n, mem_kind, flags, &win32));
-    TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dclean, dtaps));
-    TRY(xambg_device(c, dref, dclean, n, range_bins, freq_bins, win32, nullptr, 0, dmap));
+    bool refw_ready = false;
+    TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dclean, dtaps, win32, &refw_ready));
+    TRY(xambg_device(c, dref, dclean, n, range_bins, freq_bins, win32, nullptr, 0, dmap, refw_ready));
     if (mem_kind == PRC_MEM_HOST) {
         CU(cudaMemcpyAsync(out_map, c->out.p, ob, cudaMemcpyDeviceToHost, c->stream));
         if (taps_out)

@@ -48,9 +48,10 @@ constexpr int A_SBO = (ROW / 64) * ATOM_BYTES;    // stride between the two 8-ro
 constexpr int B_SBO = (NPASS / 64) * ATOM_BYTES;  // ... of a B tile
 constexpr int MN_LBO = ATOM_BYTES;                // stride between 64-element MN groups
 constexpr int NUM_EPI_WARPS = 4, NUM_LOAD_WARPS = 4;
-constexpr int THREADS = 32 * (NUM_EPI_WARPS + 1 + NUM_LOAD_WARPS);
+constexpr int THREADS = 32 * (NUM_EPI_WARPS + 1 + NUM_LOAD_WARPS + NUM_EPI_WARPS);   // 13 warps
 static_assert(STAGES == NUM_LOAD_WARPS, "loader warp w owns pipeline stage w");
 constexpr int SKEW_FLOATS = 32 * 33 + 32;          // per-warp transpose buffer (row stride 33)
+constexpr int EPI_PARTS = 2 * NUM_EPI_WARPS;       // warps 0-3 take accumulator columns [0,128), warps 9-12 [128,256)
 constexpr int TMEM_COLS = 2 * NPASS;   // [0,256): b0*b0' products, [256,512): the five cross terms
 
 struct ToepParams {
@@ -59,9 +60,11 @@ struct ToepParams {
     int nk;                 // K-steps (of 16 rows = 1024 complex samples) in the signal
     int nlag;               // complex lags wanted: 0 .. nlag-1
     int npass;              // ceil(2*(64+nlag) / 256)
-    int ranges;             // CTAs per (problem, pass): gridDim.x = 2 * npass * ranges
+    int ranges;             // LS mode: CTAs per (problem, pass): gridDim.x = 2 * npass * ranges
+    int kb;                 // block mode (> 0): K-steps per block; items = nblk * npass, any gridDim.x
+    int nblk;
     int HT;                 // row length of the partial buffer (padded lag count)
-    float2* partial;        // [problem][pass*ranges + range][HT]
+    float2* partial;        // LS: [problem][pass*ranges + range][HT];  block mode: [blk][pass][HT]
     float* debug_tile;      // optional: raw 128x256 accumulator of CTA 0
     long long* debug_clk;   // optional: phase timestamps of CTA 0
 };
@@ -157,195 +160,278 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 struct __align__(16) ToepShared {
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
-    uint64_t tmem_full;
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
 };
 
-// dynamic shared memory: [stages x {A_b0, A_b1, A_b2, B_b0, B_b1, B_b2}] [epilogue: 4 x 32x32 floats skew] [4 x 2 x HT floats]
+// One unit of work of a CTA: an accumulation over K-steps [kbeg, kbeg + kcount) for one (problem, pass),
+// whose diagonal sums go to partial row `row`.
+struct ToepItem {
+    int valid, prob, pass, kbeg, kcount;
+    long long row;
+};
+
+// LS mode (kb == 0): item = blockIdx.x only; (problem, pass, K-range) as in ToepParams.
+// Block mode (kb > 0): items blockIdx.x, blockIdx.x + gridDim.x, ... < nblk * npass; item id = blk * npass + pass,
+// K-steps [blk * kb, (blk + 1) * kb), row = item id.
+__device__ __forceinline__ ToepItem toep_item(const ToepParams& p, int it) {
+    ToepItem r;
+    if (p.kb == 0) {
+        const int per_prob = p.npass * p.ranges;
+        const int prob = blockIdx.x / per_prob;
+        const int rem = blockIdx.x - prob * per_prob;
+        const int pass = rem / p.ranges;
+        const int range = rem - pass * p.ranges;
+        r.valid = (it == 0);
+        r.prob = prob;
+        r.pass = pass;
+        r.kbeg = (int)(((long long)p.nk * range) / p.ranges);
+        r.kcount = (int)(((long long)p.nk * (range + 1)) / p.ranges) - r.kbeg;
+        r.row = (long long)prob * per_prob + rem;
+    } else {
+        const long long id = (long long)blockIdx.x + (long long)it * gridDim.x;
+        r.valid = id < (long long)p.nblk * p.npass;
+        const int blk = (int)(id / p.npass);
+        r.prob = 0;
+        r.pass = (int)(id - (long long)blk * p.npass);
+        r.kbeg = blk * p.kb;
+        r.kcount = p.kb;
+        r.row = id;
+    }
+    return r;
+}
+
+// DUAL: one item per CTA, the dominant b0*b0' chain and the five cross terms in separate accumulators
+// (long K ranges: LS correlations).  !DUAL: many short items per CTA, one accumulator per item, TMEM double
+// buffered so the diagonal-sum epilogue of item i overlaps the MMAs of item i + 1 (CAF Doppler blocks).
+// Warps 0-3 and 9-12: epilogue; warp 4: MMA issue; warps 5-8: loaders.
+// dynamic shared memory: [stages x {A_b0, A_b1, A_b2, B_b0, B_b1, B_b2}] [8 x skew] [8 x 2 x HT floats]
+template <bool DUAL>
 __global__ void __launch_bounds__(THREADS, 1) toepcorr_kernel(const __grid_constant__ ToepParams p) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     __shared__ ToepShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- work assignment
-    const int per_prob = p.npass * p.ranges;
-    const int prob = blockIdx.x / per_prob;
-    const int rem = blockIdx.x - prob * per_prob;
-    const int pass = rem / p.ranges;
-    const int range = rem - pass * p.ranges;
-    const int k0 = (int)(((long long)p.nk * range) / p.ranges);
-    const int k1 = (int)(((long long)p.nk * (range + 1)) / p.ranges);
-    const int T = k1 - k0;
+    const bool is_loader = warp > NUM_EPI_WARPS && warp <= NUM_EPI_WARPS + NUM_LOAD_WARPS;
+    const bool is_mma = warp == NUM_EPI_WARPS;
 
     uint8_t* stage_base = tsm;
-    float* skew = reinterpret_cast<float*>(tsm + STAGES * STAGE_BYTES);           // [4][32*32]
-    float* cacc = skew + NUM_EPI_WARPS * SKEW_FLOATS;                                       // [4][2][HT]
+    float* skew = reinterpret_cast<float*>(tsm + STAGES * STAGE_BYTES);           // [8][SKEW_FLOATS]
+    float* cacc = skew + EPI_PARTS * SKEW_FLOATS;                                    // [8][2][HT]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
-        mbar_init(&sh.tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], EPI_PARTS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == NUM_EPI_WARPS) tmem_alloc(&sh.tmem_base, TMEM_COLS);
-    for (int i = threadIdx.x; i < NUM_EPI_WARPS * 2 * p.HT; i += blockDim.x) cacc[i] = 0.f;
+    if (is_mma) tmem_alloc(&sh.tmem_base, TMEM_COLS);
+    for (int i = threadIdx.x; i < EPI_PARTS * 2 * p.HT; i += blockDim.x) cacc[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sh.tmem_base;
     if (p.debug_clk && blockIdx.x == 0 && threadIdx.x == 0) p.debug_clk[0] = clock64();
 
-    if (warp > NUM_EPI_WARPS) {
-        // ======================= loaders: 16-byte cp.async into the canonical MN-major tiles.
-        // Loader warp w owns pipeline stage w (K-steps t = w, w + 4, ...): it issues the whole 36 KB
-        // stage, waits for ITS copies only, publishes them to the async proxy and arrives.  (A fence
-        // after cp.async.wait_group N > 0 also waits for the younger groups of the same thread and
-        // collapses the pipeline -- measured 2300 cycles per stage instead of ~600.)
+    if (is_loader) {
+        // ======================= loaders: 16-byte cp.async into 128B-swizzled MN-major tiles.
+        // Loader warp w owns pipeline stage w: it issues the whole 36 KB stage, waits for ITS copies only,
+        // publishes them to the async proxy and arrives.  (A fence after cp.async.wait_group N > 0 also
+        // waits for the younger groups of the same thread and collapses the pipeline: measured 2300
+        // cycles per stage instead of ~600.)
         const int lw = warp - NUM_EPI_WARPS - 1;                 // 0..3 = stage
         const int ch = lane & 7;                                 // 16-byte chunk inside a 128-byte row
         const int r4 = lane >> 3;                                // 0..3: row inside a group of four
-        for (int t = lw; t < T; t += STAGES) {
-            if (t >= STAGES) mbar_wait(&sh.empty[lw], ((t / STAGES) - 1) & 1);
-            uint8_t* st = stage_base + lw * STAGE_BYTES;
-            const size_t rowbase = (size_t)(k0 + t) * KSTEP;
+        int g = 0;                                               // K-steps issued by the CTA so far
+        for (int it = 0;; ++it) {
+            const ToepItem item = toep_item(p, it);
+            if (!item.valid) break;
+            for (int t = 0; t < item.kcount; ++t, ++g) {
+                if ((g & (STAGES - 1)) != lw) continue;
+                if (g >= STAGES) mbar_wait(&sh.empty[lw], ((g / STAGES) - 1) & 1);
+                uint8_t* st = stage_base + lw * STAGE_BYTES;
+                const size_t rowbase = (size_t)(item.kbeg + t) * KSTEP;
 #pragma unroll
-            for (int pl = 0; pl < NPLANE; ++pl) {
-                uint8_t* dstA = st + pl * A_BYTES;
-                uint8_t* dstB = st + NPLANE * A_BYTES + pl * B_BYTES;
+                for (int pl = 0; pl < NPLANE; ++pl) {
+                    uint8_t* dstA = st + pl * A_BYTES;
+                    uint8_t* dstB = st + NPLANE * A_BYTES + pl * B_BYTES;
 #pragma unroll
-                for (int rr = 0; rr < KSTEP; rr += 4) {          // four K-rows per warp instruction
-                    const int row = rr + r4;                     // 0..15
-                    const int g = row >> 3, r8 = row & 7;
-                    const uint32_t swz = (uint32_t)((ch ^ r8) << 4) + (uint32_t)r8 * 128;
-                    const uint16_t* srcA = p.x[pl] + (rowbase + row) * ROW + 8 * ch;
+                    for (int rr = 0; rr < KSTEP; rr += 4) {      // four K-rows per warp instruction
+                        const int row = rr + r4;                 // 0..15
+                        const int gk = row >> 3, r8 = row & 7;
+                        const uint32_t swz = (uint32_t)((ch ^ r8) << 4) + (uint32_t)r8 * 128;
+                        const uint16_t* srcA = p.x[pl] + (rowbase + row) * ROW + 8 * ch;
 #pragma unroll
-                    for (int m = 0; m < ROW / 64; ++m) cp_async16(dstA + g * A_SBO + m * MN_LBO + swz, srcA + 64 * m);
-                    const uint16_t* srcB = p.s[prob][pl] + (rowbase + row) * ROW + (size_t)pass * NPASS + 8 * ch;
+                        for (int m = 0; m < ROW / 64; ++m) cp_async16(dstA + gk * A_SBO + m * MN_LBO + swz, srcA + 64 * m);
+                        const uint16_t* srcB = p.s[item.prob][pl] + (rowbase + row) * ROW + (size_t)item.pass * NPASS + 8 * ch;
 #pragma unroll
-                    for (int m = 0; m < NPASS / 64; ++m) cp_async16(dstB + g * B_SBO + m * MN_LBO + swz, srcB + 64 * m);
+                        for (int m = 0; m < NPASS / 64; ++m) cp_async16(dstB + gk * B_SBO + m * MN_LBO + swz, srcB + 64 * m);
+                    }
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.full[lw]);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.full[lw]);
         }
-    } else if (warp == NUM_EPI_WARPS) {
+    } else if (is_mma) {
         // ======================= MMA issuer (one elected lane)
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, NPASS);
-            for (int t = 0; t < T; ++t) {
-                const int s = t % STAGES;
-                const long long w0 = clock64();
-                mbar_wait(&sh.full[s], (t / STAGES) & 1);
+            int g = 0;
+            for (int it = 0;; ++it) {
+                const ToepItem item = toep_item(p, it);
+                if (!item.valid) break;
+                const int buf = DUAL ? 0 : (it & 1);
+                if (!DUAL && it >= 2) mbar_wait(&sh.tmem_empty[buf], ((it >> 1) - 1) & 1);
                 tc_fence_after();
-                if (p.debug_clk && blockIdx.x == 0) { p.debug_clk[5] += clock64() - w0; if (t == 0) p.debug_clk[1] = clock64(); }
-                const uint32_t a0 = smem_u32(stage_base + s * STAGE_BYTES);
-                const uint32_t b0 = a0 + NPLANE * A_BYTES;
-                uint64_t da[NPLANE], db[NPLANE];
+                const uint32_t acc0 = tmem + (DUAL ? 0 : buf * NPASS);
+                const uint32_t acc1 = DUAL ? tmem + NPASS : acc0;
+                for (int t = 0; t < item.kcount; ++t, ++g) {
+                    const int s = g & (STAGES - 1);
+                    mbar_wait(&sh.full[s], (g / STAGES) & 1);
+                    tc_fence_after();
+                    if (p.debug_clk && blockIdx.x == 0 && g == 0) p.debug_clk[1] = clock64();
+                    const uint32_t a0 = smem_u32(stage_base + s * STAGE_BYTES);
+                    const uint32_t b0 = a0 + NPLANE * A_BYTES;
+                    uint64_t da[NPLANE], db[NPLANE];
 #pragma unroll
-                for (int pl = 0; pl < NPLANE; ++pl) {
-                    da[pl] = make_desc_sw128(a0 + pl * A_BYTES, MN_LBO, A_SBO);
-                    db[pl] = make_desc_sw128(b0 + pl * B_BYTES, MN_LBO, B_SBO);
+                    for (int pl = 0; pl < NPLANE; ++pl) {
+                        da[pl] = make_desc_sw128(a0 + pl * A_BYTES, MN_LBO, A_SBO);
+                        db[pl] = make_desc_sw128(b0 + pl * B_BYTES, MN_LBO, B_SBO);
+                    }
+                    // The tensor core truncates once per MMA when it adds into the fp32 accumulator (measured
+                    // bias ~ -steps * 2^-25 relative).  DUAL keeps the dominant b0*b0' chain alone in
+                    // accumulator 0 (one truncation per K-step); the five 2^-8-smaller cross terms go to
+                    // accumulator 1 where their truncations are 256x smaller.
+                    umma_f16(acc0, da[0], db[0], idesc, t > 0);
+                    umma_f16(acc1, da[0], db[1], idesc, DUAL ? (t > 0) : 1);
+                    umma_f16(acc1, da[1], db[0], idesc, 1);
+                    umma_f16(acc1, da[0], db[2], idesc, 1);
+                    umma_f16(acc1, da[2], db[0], idesc, 1);
+                    umma_f16(acc1, da[1], db[1], idesc, 1);
+                    umma_commit(&sh.empty[s]);                   // frees the stage when these MMAs retire
                 }
-                // The tensor core truncates once per MMA when it adds into the fp32 accumulator
-                // (measured bias ~ -steps * 2^-25 relative).  Keep the dominant b0*b0' chain alone
-                // in accumulator 0 (one truncation per K-step) and the five 2^-8-smaller cross
-                // terms in accumulator 1, where their truncations are 256x smaller.
-                umma_f16(tmem, da[0], db[0], idesc, t > 0);
-                umma_f16(tmem + NPASS, da[0], db[1], idesc, t > 0);
-                umma_f16(tmem + NPASS, da[1], db[0], idesc, 1);
-                umma_f16(tmem + NPASS, da[0], db[2], idesc, 1);
-                umma_f16(tmem + NPASS, da[2], db[0], idesc, 1);
-                umma_f16(tmem + NPASS, da[1], db[1], idesc, 1);
-                umma_commit(&sh.empty[s]);                       // frees the stage when these MMAs retire
+                umma_commit(&sh.tmem_full[buf]);
+                if (p.debug_clk && blockIdx.x == 0) { p.debug_clk[2] = clock64(); if (it < 8) p.debug_clk[16 + it] = clock64(); }
             }
-            umma_commit(&sh.tmem_full);
-            if (p.debug_clk && blockIdx.x == 0) p.debug_clk[2] = clock64();
         }
         __syncwarp();
     } else {
-        // ======================= epilogue: TMEM -> diagonal sums
-        mbar_wait(&sh.tmem_full, 0);
-        tc_fence_after();
-        if (p.debug_clk && blockIdx.x == 0 && threadIdx.x == 0) p.debug_clk[3] = clock64();
-        float* sk = skew + warp * SKEW_FLOATS;
-        float* cre = cacc + (warp * 2 + 0) * p.HT;
-        float* cim = cacc + (warp * 2 + 1) * p.HT;
-        for (int j0 = 0; j0 < NPASS; j0 += 32) {
-            uint32_t v[32], v2[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)j0, v);
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(NPASS + j0), v2);
+        // ======================= epilogue (8 warps): TMEM -> diagonal sums -> one partial row per item
+        const int part = warp < NUM_EPI_WARPS ? warp : NUM_EPI_WARPS + (warp - (NUM_EPI_WARPS + 1 + NUM_LOAD_WARPS));
+        const int quad = warp & 3;                               // TMEM lane quadrant this warp may touch
+        const int jbeg = part < NUM_EPI_WARPS ? 0 : NPASS / 2, jend = jbeg + NPASS / 2;
+        const int etid = part * 32 + lane;                       // 0..255 among the epilogue threads
+        float* sk = skew + part * SKEW_FLOATS;
+        float* cre = cacc + (part * 2 + 0) * p.HT;
+        float* cim = cacc + (part * 2 + 1) * p.HT;
+        for (int it = 0;; ++it) {
+            const ToepItem item = toep_item(p, it);
+            if (!item.valid) break;
+            const int buf = DUAL ? 0 : (it & 1);
+            mbar_wait(&sh.tmem_full[buf], DUAL ? 0 : ((it >> 1) & 1));
+            tc_fence_after();
+            if (p.debug_clk && blockIdx.x == 0 && etid == 0 && it == 0) p.debug_clk[3] = clock64();
+            const uint32_t acc0 = tmem + (DUAL ? 0 : buf * NPASS);
+            for (int j0 = jbeg; j0 < jend; j0 += 32) {
+                // real diagonal delta = base + dd - 31, dd = jj - l + 31 in [0, 62]; wanted: -1 <= delta <= 2*nlag - 1
+                const int base = item.pass * NPASS + j0 - quad * 32;
+                if (base + 31 < -1 || base - 31 > 2 * p.nlag - 1) continue;      // tile entirely outside the lag band
+                const bool dbg = p.debug_clk && blockIdx.x == 0 && etid == 0 && it == 0 && j0 == jbeg + 32;
+                if (dbg) p.debug_clk[8] = clock64();
+                uint32_t v[32];
+                tmem_ld32(acc0 + ((uint32_t)(quad * 32) << 16) + (uint32_t)j0, v);
+                if (dbg) p.debug_clk[9] = clock64();
+                if (DUAL) {
+                    uint32_t v2[32];
+                    tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(NPASS + j0), v2);
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
-            if (p.debug_tile && blockIdx.x == 0) {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj) p.debug_tile[(warp * 32 + lane) * NPASS + j0 + jj] = __uint_as_float(v[jj]);
-            }
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) sk[jj * 33 + lane] = __uint_as_float(v[jj]);   // row stride 33: both phases conflict-free
-            __syncwarp();
-            // real diagonal delta = base + dd - 31, dd = jj - l + 31
-            const int base = pass * NPASS + j0 - warp * 32;
-            float se[2], so[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int dd = lane + 32 * h;
-                float e = 0.f, o = 0.f;
-#pragma unroll
-                for (int l = 0; l < 32; ++l) {               // fixed trip count: the 32 loads pipeline
-                    const int jj = dd - 31 + l;
-                    const float val = (jj >= 0 && jj < 32) ? sk[(jj & 31) * 33 + l] : 0.f;
-                    if (l & 1) o += val; else e += val;
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
                 }
-                se[h] = e;
-                so[h] = o;
-            }
-            // phase 1: even diagonals -> real part, odd diagonals (odd rows) -> +imag[(delta+1)/2]
+                if (p.debug_tile && blockIdx.x == 0 && it == 0) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int dd = lane + 32 * h;
-                const int delta = base + dd - 31;
-                if (dd <= 62) {
-                    if ((delta & 1) == 0) {
-                        const int d = delta >> 1;
-                        if (delta >= 0 && d < p.nlag) cre[d] += se[h] + so[h];
-                    } else {
-                        const int d = (delta + 1) >> 1;
-                        if (delta + 1 >= 0 && d < p.nlag) cim[d] += so[h];
+                    for (int jj = 0; jj < 32; ++jj) p.debug_tile[(quad * 32 + lane) * NPASS + j0 + jj] = __uint_as_float(v[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) sk[jj * 33 + lane] = __uint_as_float(v[jj]);   // row stride 33: both phases conflict-free
+                __syncwarp();
+                if (dbg) p.debug_clk[10] = clock64();
+                // For row l this lane needs column jj = dd - 31 + l of exactly one of its two diagonals
+                // (dd = lane: valid when l >= 31 - lane; dd = lane + 32: valid when l <= 30 - lane), so one
+                // load per row feeds both sums: 32 pipelined loads instead of 64 half-masked ones.
+                float se[2] = {0.f, 0.f}, so[2] = {0.f, 0.f};
+#pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    const float val = sk[((lane + l + 1) & 31) * 33 + l];
+                    const bool hi = (l + lane <= 30);            // belongs to dd = lane + 32
+                    if (l & 1) { so[1] += hi ? val : 0.f; so[0] += hi ? 0.f : val; }
+                    else       { se[1] += hi ? val : 0.f; se[0] += hi ? 0.f : val; }
+                }
+                if (dbg) p.debug_clk[11] = clock64() + (long long)(se[0] + so[0] + se[1] + so[1] == 12345.678f);
+                // Scatter into this warp's private sums, branch-free (divergent read-modify-writes cost ~1000
+                // cycles per tile).  base is even, so delta = base + dd - 31 is even exactly on odd lanes:
+                //   odd lane : re[delta/2] += se + so
+                //   even lane: im[(delta+1)/2] += so   (odd rows)   then   im[(delta-1)/2] -= se   (even rows)
+                // Within a round all target addresses differ (dd and dd + 32 are 16 lags apart).
+                {
+                    const bool oddl = lane & 1;
+                    float* tgt[2];
+                    float val[2];
+                    bool ok[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int dd = lane + 32 * h;
+                        const int delta = base + dd - 31;
+                        const int d = oddl ? (delta >> 1) : ((delta + 1) >> 1);
+                        ok[h] = dd <= 62 && (oddl ? delta >= 0 : delta + 1 >= 0) && d < p.nlag;
+                        tgt[h] = (oddl ? cre : cim) + (ok[h] ? d : 0);
+                        val[h] = oddl ? se[h] + so[h] : so[h];
                     }
-                }
-            }
-            __syncwarp();
-            // phase 2: odd diagonals (even rows) -> -imag[(delta-1)/2]
+                    const float c0 = ok[0] ? *tgt[0] : 0.f, c1 = ok[1] ? *tgt[1] : 0.f;
+                    if (ok[0]) *tgt[0] = c0 + val[0];
+                    if (ok[1]) *tgt[1] = c1 + val[1];
+                    __syncwarp();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int dd = lane + 32 * h;
-                const int delta = base + dd - 31;
-                if (dd <= 62 && (delta & 1)) {
-                    const int d = (delta - 1) >> 1;
-                    if (delta - 1 >= 0 && d < p.nlag) cim[d] -= se[h];
+                    for (int h = 0; h < 2; ++h) {
+                        const int dd = lane + 32 * h;
+                        const int delta = base + dd - 31;
+                        const int d = (delta - 1) >> 1;
+                        ok[h] = !oddl && dd <= 62 && delta - 1 >= 0 && d < p.nlag;
+                        tgt[h] = cim + (ok[h] ? d : 0);
+                    }
+                    const float e0 = ok[0] ? *tgt[0] : 0.f, e1 = ok[1] ? *tgt[1] : 0.f;
+                    if (ok[0]) *tgt[0] = e0 - se[0];
+                    if (ok[1]) *tgt[1] = e1 - se[1];
+                    __syncwarp();
                 }
+                if (dbg) p.debug_clk[12] = clock64();
             }
+            tc_fence_before();
             __syncwarp();
+            if (!DUAL && lane == 0) mbar_arrive(&sh.tmem_empty[buf]);        // this accumulator may be overwritten
+            // combine the eight parts, write the row, clear the sums for the next item
+            asm volatile("bar.sync 2, %0;" ::"n"(EPI_PARTS * 32));
+            float2* out = p.partial + (size_t)item.row * (size_t)p.HT;
+            for (int l = etid; l < p.HT; l += EPI_PARTS * 32) {
+                float re = 0.f, im = 0.f;
+#pragma unroll
+                for (int w = 0; w < EPI_PARTS; ++w) {
+                    re += cacc[(w * 2 + 0) * p.HT + l];
+                    im += cacc[(w * 2 + 1) * p.HT + l];
+                    cacc[(w * 2 + 0) * p.HT + l] = 0.f;
+                    cacc[(w * 2 + 1) * p.HT + l] = 0.f;
+                }
+                out[l] = make_float2(re, im);
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(EPI_PARTS * 32));
+            if (p.debug_clk && blockIdx.x == 0 && etid == 0) { if (it == 0) p.debug_clk[4] = clock64(); if (it < 8) p.debug_clk[24 + it] = clock64(); }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
-    if (p.debug_clk && blockIdx.x == 0 && threadIdx.x == 0) p.debug_clk[4] = clock64();
-    // ---- combine the four epilogue warps and write the partial row
-    float2* out = p.partial + ((size_t)prob * per_prob + rem) * (size_t)p.HT;
-    for (int l = threadIdx.x; l < p.HT; l += blockDim.x) {
-        float re = 0.f, im = 0.f;
-#pragma unroll
-        for (int w = 0; w < NUM_EPI_WARPS; ++w) {
-            re += cacc[(w * 2 + 0) * p.HT + l];
-            im += cacc[(w * 2 + 1) * p.HT + l];
-        }
-        out[l] = make_float2(re, im);
-    }
-    if (warp == NUM_EPI_WARPS) {
+    if (is_mma) {
         tc_fence_after();
         tmem_dealloc(tmem, TMEM_COLS);
     }
@@ -388,8 +474,72 @@ __global__ void bf16_split_kernel(const float2* __restrict__ sig, int n, int dmi
     reinterpret_cast<uint32_t*>(p2)[q] = (uint32_t)o[2][0] | ((uint32_t)o[2][1] << 16);
 }
 
+// Fused per-frame preparation (one launch, blockIdx.y = signal): BF16 planes of ref (circular
+// extension, also the x operand when n is a multiple of 1024) and of srv rotated by -peek; while ref is
+// in registers, optionally emit refw = ref * window for the CAF.  Four samples per thread, loads first.
+struct PrepParams {
+    const float2* sig[2];
+    int dmin[2];
+    int zero_outside[2];    // 1: samples outside [0, n) are zero (x operand); 0: circular (s operand)
+    uint16_t* plane[2][3];
+    const float* win;       // optional
+    float2* refw;           // optional: ref * win for q < n
+    int n;
+    long long len;
+};
+
+__global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ PrepParams p) {
+    const int sg = blockIdx.y;
+    const long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q0 >= p.len) return;
+    const float2* __restrict__ sig = p.sig[sg];
+    long long i0 = (q0 + p.dmin[sg]) % p.n;
+    if (i0 < 0) i0 += p.n;
+    float2 v[4];
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        long long i = i0 + k;
+        if (i >= p.n) i -= p.n;
+        if (i >= p.n) i %= p.n;
+        const long long lin = q0 + k + p.dmin[sg];           // un-wrapped sample index
+        const bool ok = (q0 + k < p.len) && (!p.zero_outside[sg] || (lin >= 0 && lin < p.n));
+        v[k] = ok ? sig[i] : make_float2(0.f, 0.f);
+        w[k] = (sg == 0 && p.refw && q0 + k < p.n) ? p.win[q0 + k] : 1.f;
+    }
+    uint32_t o[3][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float c[2] = {v[k].x, v[k].y};
+        uint16_t b[3][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const uint16_t a0 = bf16_rn_bits(c[e]);
+            const float r1 = c[e] - bf16_bits_to_float(a0);
+            const uint16_t a1 = bf16_rn_bits(r1);
+            const float r2 = r1 - bf16_bits_to_float(a1);
+            b[0][e] = a0; b[1][e] = a1; b[2][e] = bf16_rn_bits(r2);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) o[pl][k] = (uint32_t)b[pl][0] | ((uint32_t)b[pl][1] << 16);
+    }
+    if (q0 + 3 < p.len) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+            reinterpret_cast<uint4*>(p.plane[sg][pl])[q0 / 4] = make_uint4(o[pl][0], o[pl][1], o[pl][2], o[pl][3]);
+    } else {
+        for (int k = 0; k < 4 && q0 + k < p.len; ++k)
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) reinterpret_cast<uint32_t*>(p.plane[sg][pl])[q0 + k] = o[pl][k];
+    }
+    if (sg == 0 && p.refw) {
+        for (int k = 0; k < 4; ++k)
+            if (q0 + k < p.n) p.refw[q0 + k] = make_float2(v[k].x * w[k], v[k].y * w[k]);
+    }
+}
+
 inline size_t toep_smem_bytes(int HT) {
-    return (size_t)STAGES * STAGE_BYTES + NUM_EPI_WARPS * SKEW_FLOATS * sizeof(float) + (size_t)NUM_EPI_WARPS * 2 * HT * sizeof(float);
+    return (size_t)STAGES * STAGE_BYTES + EPI_PARTS * SKEW_FLOATS * sizeof(float) + (size_t)EPI_PARTS * 2 * HT * sizeof(float);
 }
 
 }  // namespace tc

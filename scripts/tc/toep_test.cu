@@ -51,20 +51,42 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 3; ++k) { p.x[k] = xp[k]; p.s[0][k] = s0p[k]; p.s[1][k] = s1p[k]; }
     p.nk = nk; p.nlag = nlag; p.npass = npass; p.ranges = ranges; p.HT = HT;
     p.partial = dpart; p.debug_tile = dbg;
-    long long* dclk; CK(cudaMalloc(&dclk, 64)); CK(cudaMemset(dclk, 0, 64)); p.debug_clk = dclk;
+    long long* dclk; CK(cudaMalloc(&dclk, 512)); CK(cudaMemset(dclk, 0, 512)); p.debug_clk = dclk;
+    if (argc > 4 && atoi(argv[4]) > 0) {
+        // block mode (CAF-like): x = ref planes, s = srv planes, nblk blocks of kb K-steps, persistent grid of 148 CTAs
+        ToepParams q = p;
+        q.kb = atoi(argv[4]); q.nblk = nk / q.kb; q.ranges = 0; q.debug_tile = nullptr;
+        for (int k = 0; k < 3; ++k) q.s[0][k] = s1p[k];
+        float2* dp2; CK(cudaMalloc(&dp2, (size_t)q.nblk * npass * HT * sizeof(float2))); q.partial = dp2;
+        CK(cudaFuncSetAttribute(toepcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)toep_smem_bytes(HT)));
+        cudaEvent_t a0, a1; cudaEventCreate(&a0); cudaEventCreate(&a1);
+        for (int rep = 0; rep < 3; ++rep) {
+            CK(cudaMemset(dclk, 0, 512));
+            cudaEventRecord(a0);
+            toepcorr_kernel<false><<<148, THREADS, toep_smem_bytes(HT)>>>(q);
+            cudaEventRecord(a1);
+            CK(cudaDeviceSynchronize());
+        }
+        float ms2; cudaEventElapsedTime(&ms2, a0, a1);
+        long long hc[64]; CK(cudaMemcpy(hc, dclk, 512, cudaMemcpyDeviceToHost));
+        printf("block mode: nblk=%d kb=%d items=%d kernel %.2f us\n", q.nblk, q.kb, q.nblk * npass, ms2 * 1e3);
+        for (int it = 0; it < 7; ++it) printf("  item %d: MMA committed at %lld, epilogue done at %lld\n", it, hc[16 + it] - hc[0], hc[24 + it] - hc[0]);
+        CK(cudaMemset(dclk, 0, 512));
+    }
     const size_t smem = toep_smem_bytes(HT);
-    CK(cudaFuncSetAttribute(toepcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(toepcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 4; ++rep) {
         if (rep == 1) { p.debug_tile = nullptr; }      // rep 0 dumps the tile, the timed reps do not
         cudaEventRecord(e0);
-        toepcorr_kernel<<<2 * npass * ranges, THREADS, smem>>>(p);
+        toepcorr_kernel<true><<<2 * npass * ranges, THREADS, smem>>>(p);
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
     }
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("kernel time %.3f us\n", ms * 1e3);
-    { long long hc[8]; CK(cudaMemcpy(hc, dclk, 64, cudaMemcpyDeviceToHost));
+    { long long hc[64]; CK(cudaMemcpy(hc, dclk, 512, cudaMemcpyDeviceToHost));
+      printf("unit timing (warp 0, 2nd tile): tmem_ld %lld, +add/STS %lld, +diag loads %lld, +RMW %lld cycles\n", hc[9]-hc[8], hc[10]-hc[9], hc[11]-hc[10], hc[12]-hc[11]);
       printf("CTA0 cycles: setup->first full %lld, ->last commit %lld, ->tmem_full seen %lld, ->epilogue done %lld\n", hc[1]-hc[0], hc[2]-hc[0], hc[3]-hc[0], hc[4]-hc[0]);
       printf("  MMA thread waited on full: %lld cyc; loader waited on empty: %lld cyc, on cp.async groups: %lld cyc (sums over 3 reps)\n", hc[5], hc[6], hc[7]); }
 
