@@ -114,6 +114,7 @@ struct Ctx {
     bool own_stream = false;
     int nsm = 148;
     std::mutex mu;
+    DBuf cafplane[6];         // bf16 planes of the tensor-core CAF: x[3], s[3]
     DBuf tcplane[9];          // bf16 planes of the tensor-core path: x[3], s0[3], s1[3]
     DBuf refw, ref, srv, out, clean, partial, win32, win64, dtaps32, dtaps64, lstaps, tw, pbuf, status,
         nl_init, nl_taps;
@@ -122,6 +123,7 @@ struct Ctx {
     void release() {
         cudaSetDevice(device);
         for (DBuf& b : tcplane) b.release();
+        for (DBuf& b : cafplane) b.release();
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
             b->release();
@@ -344,6 +346,30 @@ void launch_lagstream(dim3 grid, int threads, size_t smem, cudaStream_t st, cons
     }
 }
 
+// Tensor-core CAF eligibility and geometry (shared by the frame pipeline, which lets the LS stage's prep
+// and FIR kernels write the CAF operands while the data is in registers, and by xambg_device)
+struct CafTc {
+    bool on = false;
+    long long D = 0, nx = 0, slen = 0;
+    int npass = 0, ht = 0;
+    bool planes_ready = false;    // x and s planes already written by the LS stage
+};
+
+CafTc caf_tc_plan(const Ctx* c, long long n, int R, int F, bool has_taps) {
+    CafTc t;
+    if (!g_tc || !g_tc_caf || has_taps || F < 1) return t;
+    const long long D = n / F;
+    if (D < 1024 || D % 1024 != 0) return t;
+    t.npass = ceil_div(2 * (64 + R + 1), tc::NPASS);
+    t.ht = ceil_div(R + 1, 2) * 2;
+    if ((long long)F * t.npass < c->nsm || tc::toep_smem_bytes(t.ht) > SMEM_LIMIT) return t;
+    t.on = true;
+    t.D = D;
+    t.nx = (long long)F * D;
+    t.slen = t.nx + (long long)t.npass * 128;
+    return t;
+}
+
 // --------------------------------------------------------------------------- device pipelines
 // All pointers are device pointers; everything is enqueued on c->stream.
 
@@ -356,7 +382,7 @@ int decimator_offset(long long ntaps, long long D) {   // resample_poly alignmen
 
 int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int R, int F,
                  const float* win32, const float* dtaps32, long long ndtaps, float2* out,
-                 bool refw_ready = false) {
+                 bool refw_ready = false, bool caf_planes_ready = false) {
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
     if (F < 1 || R < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", F, R);
     const long long D = n / F;
@@ -379,10 +405,8 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     Geo g{};
     long long d_per_cta = 0;
     const float2* bnd_x = nullptr;                  // boundary-sample correction of the tensor-core path
-    const int caf_npass = ceil_div(2 * (64 + R + 1), tc::NPASS);
-    const int caf_ht = ceil_div(R + 1, 2) * 2;
-    if (g_tc && g_tc_caf && taps == nullptr && D >= 1024 && D % 1024 == 0 && ntaps == D + 1 && c0 == D / 2 &&
-        (long long)F * caf_npass >= c->nsm && tc::toep_smem_bytes(caf_ht) <= SMEM_LIMIT) {
+    const CafTc ct = (ntaps == D + 1 && c0 == D / 2) ? caf_tc_plan(c, n, R, F, taps != nullptr) : CafTc{};
+    if (ct.on) {
         // ---- tensor-core CAF: one (Doppler block, pass) item per accumulation, persistent CTAs
         const float2* xw = ref;
         if (win32 && refw_ready) {
@@ -396,48 +420,44 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
             TRY(check_launch("weight_kernel"));
             xw = c->refw.as<float2>();
         }
-        const long long nx = (long long)F * D;
-        const long long slen = nx + (long long)caf_npass * 128;
-        for (int k = 0; k < 6; ++k) TRY(c->tcplane[k].ensure((size_t)(k < 3 ? nx : slen) * 2 * sizeof(uint16_t)));
-        TRY(c->partial.ensure((size_t)F * caf_npass * caf_ht * sizeof(float2)));
-        tc::PrepParams pp{};
-        pp.sig[0] = xw; pp.sig[1] = srv;
-        pp.dmin[0] = -(int)(D / 2); pp.dmin[1] = -(int)(D / 2);
-        pp.zero_outside[0] = 1; pp.zero_outside[1] = 0;
-        for (int k = 0; k < 3; ++k) { pp.plane[0][k] = c->tcplane[k].as<uint16_t>(); pp.plane[1][k] = c->tcplane[3 + k].as<uint16_t>(); }
-        pp.win = nullptr; pp.refw = nullptr;
-        pp.n = (int)n;
-        pp.len = slen;                       // the x planes are only read below nx; both are sized >= what is written
-        // x planes hold nx samples: run the x signal with its own length
-        {
-            ProfScope ps(c, K_MISC);
-            tc::PrepParams px = pp;
-            px.len = nx;
-            px.sig[1] = xw; px.plane[1][0] = pp.plane[0][0]; px.plane[1][1] = pp.plane[0][1]; px.plane[1][2] = pp.plane[0][2];
-            tc::tc_prep_kernel<<<dim3(ceil_div(nx, 1024), 1), 256, 0, c->stream>>>(px);
-            tc::PrepParams py = pp;
-            py.sig[0] = srv; py.zero_outside[0] = 0;
-            for (int k = 0; k < 3; ++k) py.plane[0][k] = pp.plane[1][k];
-            tc::tc_prep_kernel<<<dim3(ceil_div(slen, 1024), 1), 256, 0, c->stream>>>(py);
+        for (int k = 0; k < 6; ++k) TRY(c->cafplane[k].ensure((size_t)(k < 3 ? ct.nx : ct.slen) * 2 * sizeof(uint16_t)));
+        TRY(c->partial.ensure((size_t)F * ct.npass * ct.ht * sizeof(float2)));
+        if (!caf_planes_ready) {
+            tc::PrepParams px{};
+            px.sig[0] = xw; px.sig[1] = xw;
+            px.dmin[0] = px.dmin[1] = -(int)(D / 2);
+            px.zero_outside[0] = px.zero_outside[1] = 1;
+            for (int k = 0; k < 3; ++k) px.plane[0][k] = px.plane[1][k] = c->cafplane[k].as<uint16_t>();
+            px.n = (int)n;
+            px.len = ct.nx;
+            tc::PrepParams py = px;
+            py.sig[0] = py.sig[1] = srv;
+            py.zero_outside[0] = py.zero_outside[1] = 0;
+            for (int k = 0; k < 3; ++k) py.plane[0][k] = py.plane[1][k] = c->cafplane[3 + k].as<uint16_t>();
+            py.len = ct.slen;
+            {
+                ProfScope ps(c, K_MISC);
+                tc::tc_prep_kernel<<<dim3(ceil_div(ct.nx, 1024), 1), 256, 0, c->stream>>>(px);
+                tc::tc_prep_kernel<<<dim3(ceil_div(ct.slen, 1024), 1), 256, 0, c->stream>>>(py);
+            }
+            TRY(check_launch("tc_prep_kernel(caf)"));
         }
-        TRY(check_launch("tc_prep_kernel(caf)"));
         tc::ToepParams tp{};
         for (int k = 0; k < 3; ++k) {
-            tp.x[k] = c->tcplane[k].as<uint16_t>();
-            tp.s[0][k] = c->tcplane[3 + k].as<uint16_t>();
-            tp.s[1][k] = c->tcplane[3 + k].as<uint16_t>();
+            tp.x[k] = c->cafplane[k].as<uint16_t>();
+            tp.s[0][k] = tp.s[1][k] = c->cafplane[3 + k].as<uint16_t>();
         }
-        tp.nk = (int)(nx / 1024); tp.nlag = R + 1; tp.npass = caf_npass; tp.ranges = 0;
-        tp.kb = (int)(D / 1024); tp.nblk = F; tp.HT = caf_ht;
+        tp.nk = (int)(ct.nx / 1024); tp.nlag = R + 1; tp.npass = ct.npass; tp.ranges = 0;
+        tp.kb = (int)(D / 1024); tp.nblk = F; tp.HT = ct.ht;
         tp.partial = c->partial.as<float2>();
         tp.debug_tile = nullptr; tp.debug_clk = nullptr;
         {
             ProfScope ps(c, K_LAGCORR_CAF);
-            tc::toepcorr_kernel<false><<<c->nsm, tc::THREADS, tc::toep_smem_bytes(caf_ht), c->stream>>>(tp);
+            tc::toepcorr_kernel<false><<<c->nsm, tc::THREADS, tc::toep_smem_bytes(ct.ht), c->stream>>>(tp);
         }
         TRY(check_launch("toepcorr_kernel(caf)"));
-        g.nchunk = caf_npass;
-        g.HT = caf_ht;
+        g.nchunk = ct.npass;
+        g.HT = ct.ht;
         bnd_x = xw;
     } else if (g_stream && taps == nullptr && ntaps >= 64) {   // tiny Doppler blocks: one flush per block would dominate
         StreamGeo sg;
@@ -549,8 +569,10 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
 }
 
 int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek,
-              double reg, float2* out, float2* taps_out, const float* win32 = nullptr, bool* refw_ready = nullptr) {
+              double reg, float2* out, float2* taps_out, const float* win32 = nullptr, bool* refw_ready = nullptr,
+              CafTc* caf = nullptr) {
     if (refw_ready) *refw_ready = false;
+    bool caf_x_done = false;
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
     if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
         return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
@@ -588,6 +610,15 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
             pp.refw = fold ? c->refw.as<float2>() : nullptr;
             pp.n = (int)n;
             pp.len = slen;
+            if (fold && caf && caf->on) {          // also emit the CAF x operand (ref * window, shifted by D/2)
+                for (int k = 0; k < 3; ++k) {
+                    TRY(c->cafplane[k].ensure((size_t)caf->nx * 2 * sizeof(uint16_t)));
+                    pp.cafx[k] = c->cafplane[k].as<uint16_t>();
+                }
+                pp.caf_off = caf->D / 2;
+                pp.caf_nx = caf->nx;
+                caf_x_done = true;
+            }
             tc::tc_prep_kernel<<<dim3(ceil_div(slen, 1024), 2), 256, 0, c->stream>>>(pp);
         }
         TRY(check_launch("tc_prep_kernel"));
@@ -676,6 +707,15 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
 
     FirParams fp{};
     fp.ref = ref; fp.srv = srv; fp.taps = c->lstaps.as<float2>(); fp.out = out;
+    if (caf && caf->on && caf_x_done) {           // the FIR writes the CAF s operand (cleaned channel) as well
+        for (int k = 0; k < 3; ++k) {
+            TRY(c->cafplane[3 + k].ensure((size_t)caf->slen * 2 * sizeof(uint16_t)));
+            fp.cafs[k] = c->cafplane[3 + k].as<uint16_t>();
+        }
+        fp.caf_off = caf->D / 2;
+        fp.caf_slen = caf->slen;
+        caf->planes_ready = true;
+    }
     fp.n = (int)n; fp.M = M; fp.peek = peek;
     const int mode = g_stream ? 2 : (g_packed ? 1 : 0);
     const int tk = mode == 2 ? kTiles[g_tile].ti : FIR_TK, to = mode == 2 ? kTiles[g_tile].td : FIR_TO;
@@ -1029,8 +1069,9 @@ int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_
     const float* win32;
     TRY(stage_window(c, window, n, mem_kind, flags, &win32));
     bool refw_ready = false;
-    TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dclean, dtaps, win32, &refw_ready));
-    TRY(xambg_device(c, dref, dclean, n, range_bins, freq_bins, win32, nullptr, 0, dmap, refw_ready));
+    CafTc caf = (n / freq_bins) % 2 == 0 ? caf_tc_plan(c, n, range_bins, freq_bins, false) : CafTc{};
+    TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dclean, dtaps, win32, &refw_ready, &caf));
+    TRY(xambg_device(c, dref, dclean, n, range_bins, freq_bins, win32, nullptr, 0, dmap, refw_ready, caf.planes_ready));
     if (mem_kind == PRC_MEM_HOST) {
         CU(cudaMemcpyAsync(out_map, c->out.p, ob, cudaMemcpyDeviceToHost, c->stream));
         if (taps_out)

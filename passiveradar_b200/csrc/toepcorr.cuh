@@ -486,7 +486,18 @@ struct PrepParams {
     float2* refw;           // optional: ref * win for q < n
     int n;
     long long len;
+    // optional (signal 0 only): BF16 planes of the CAF x operand, cafx[q + caf_off] = ref[q] * win[q]
+    // (zero for indices below caf_off), written for indices < caf_nx
+    uint16_t* cafx[3];
+    long long caf_off, caf_nx;
 };
+
+__device__ __forceinline__ void bf16_split3(float v, uint16_t (&b)[3]) {
+    b[0] = bf16_rn_bits(v);
+    const float r1 = v - bf16_bits_to_float(b[0]);
+    b[1] = bf16_rn_bits(r1);
+    b[2] = bf16_rn_bits(r1 - bf16_bits_to_float(b[1]));
+}
 
 __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ PrepParams p) {
     const int sg = blockIdx.y;
@@ -535,6 +546,26 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Pr
     if (sg == 0 && p.refw) {
         for (int k = 0; k < 4; ++k)
             if (q0 + k < p.n) p.refw[q0 + k] = make_float2(v[k].x * w[k], v[k].y * w[k]);
+    }
+    if (sg == 0 && p.cafx[0]) {
+        uint32_t c[3][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint16_t br[3], bi[3];
+            const bool in = q0 + k < p.n;
+            bf16_split3(in ? v[k].x * w[k] : 0.f, br);
+            bf16_split3(in ? v[k].y * w[k] : 0.f, bi);
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) c[pl][k] = (uint32_t)br[pl] | ((uint32_t)bi[pl] << 16);
+        }
+        const long long t0 = q0 + p.caf_off;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(p.cafx[pl]);
+            if (q0 < p.n && t0 + 3 < p.caf_nx) reinterpret_cast<uint4*>(dst)[t0 / 4] = make_uint4(c[pl][0], c[pl][1], c[pl][2], c[pl][3]);
+            else for (int k = 0; k < 4; ++k) if (q0 + k < p.n && t0 + k < p.caf_nx) dst[t0 + k] = c[pl][k];
+            if (q0 < p.caf_off) for (int k = 0; k < 4; ++k) if (q0 + k < p.caf_off && q0 + k < p.caf_nx) dst[q0 + k] = 0u;   // zero lead-in
+        }
     }
 }
 

@@ -279,3 +279,41 @@ def test_xambg_config4_grid_matches_oracle():
     want = xo.fast_xambg_oracle(ref, srv, 40, F, n, w)          # lags 0..40 -> columns R-40..R
     got = prb.fast_xambg(ref, srv, R, F, n, w)
     assert G.rel_inf(got[:, R - 40:, :], want) <= TOL
+
+
+# ------------------------------------------------------------------ frame pipeline (prc_frame_c64, fused path)
+@pytest.mark.parametrize("name", ["frame_c1_p0", "frame_c2_p0"])
+def test_frame_pipeline_matches_reference_golden(name):
+    """FramePipeline = the fused device-resident path bench.py times (LS stage writes the CAF operands)."""
+    from passiveradar_b200.frames import FramePipeline
+    from oracle import clutter_oracle as co
+    from oracle import xambg_oracle as xo
+    g = G.load(name)
+    ref, srv = G.inputs(g)
+    n, R, F = int(g["n"]), int(g["R"]), int(g["F"])
+    pipe = FramePipeline(n, R, F, filter_len=R, reg=1.0, peek=10, window=("kaiser", 5.0), nslots=2)
+    ref2, srv2 = synth.make_frame(n, "P1", frame=11)
+    maps = pipe.run_host(np.stack([ref, ref2, ref]), np.stack([srv, srv2, srv]))
+    assert maps.shape == (3, F, R + 1, 1) and maps.dtype == np.complex64
+    w = signal.get_window(("kaiser", 5.0), n)
+    t_clean, _ = co.ls_filter_truth(ref, srv, R, 1.0, 10)
+    t_map = xo.fast_xambg_truth(ref, t_clean, R, F, n, w)
+    e_ref = G.rel_inf(g["out"], t_map)
+    assert G.rel_inf(maps[0], t_map) <= TOL
+    assert G.rel_inf(maps[0], g["out"]) <= TOL + 1.2 * e_ref
+    assert np.array_equal(maps[0], maps[2])                   # deterministic, slot-independent
+    # second frame (clutter + target): against the separate operators
+    cleaned = prb.LS_Filter(ref2, srv2, R)
+    want = prb.fast_xambg(ref2, cleaned, R, F, n, w)
+    assert G.rel_inf(maps[1], want) <= 2e-6
+
+
+def test_frame_pipeline_without_window_and_odd_shape():
+    from passiveradar_b200.frames import FramePipeline
+    n, R, F = 50_000, 37, 24
+    ref, srv = synth.make_frame(n, "P1", frame=2)
+    pipe = FramePipeline(n, R, F, filter_len=20, reg=0.5, peek=3, window=None, nslots=1)
+    got = pipe.process(ref, srv)
+    cleaned = prb.LS_Filter(ref, srv, 20, 0.5, 3)
+    want = prb.fast_xambg(ref, cleaned, R, F)
+    assert G.rel_inf(got, want) <= 2e-6
