@@ -108,6 +108,22 @@ int prc_ls_filter_c64(const prc_c64* ref, const prc_c64* srv, int64_t n,
                       prc_c64* out, prc_c64* taps,
                       int mem_kind, int device, void* stream, unsigned flags);
 
+/* ---- Toeplitz least-squares clutter filter (what main.py actually calls) ---------------------------
+ * prc_ls_toeplitz_c64 replaces LS_Filter_Toeplitz(), reference passiveRadar/clutter_removal.py:109-160:
+ * reference rolled by -peek (:139), LINEAR (zero-padded) auto/cross correlations (:142-147), Levinson
+ * solve without regularisation (:150, float64 here as in SciPy), linear convolution + subtraction
+ * (:153-155).  prc_ls_multiple_c64 replaces LS_Filter_Multiple() (:162-187): the filter is applied once
+ * per Doppler bin on the running residual, the reference being frequency-shifted by bin Hz first
+ * (signal_utils.py:24-27, float32 phase ramp as in the reference).  doppler_bins == NULL means [0].
+ * Results are complex64; the Python wrappers widen them to complex128 like the reference returns.
+ */
+int prc_ls_toeplitz_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek,
+                        prc_c64* out, prc_c64* taps, int mem_kind, int device, void* stream, unsigned flags);
+int prc_ls_multiple_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek,
+                        double sample_rate, const double* doppler_bins, int nbins,
+                        prc_c64* out, prc_c64* taps_last,
+                        int mem_kind, int device, void* stream, unsigned flags);
+
 /* ---- NLMS / block-NLMS clutter filter ---------------------------------------------------
  * Replaces NLMS_filter(), reference passiveRadar/clutter_removal.py:189-249
  * (block_len == 1) and provides block_NLMS (block_len > 1; not in the reference,

@@ -175,3 +175,47 @@ def block_nlms_oracle_c(ref, srv, filter_len, mu, peek=10, block_len=1, initial_
     if st != 0:
         raise MemoryError("nlms_oracle_c64 failed")
     return out, taps
+
+
+# ------------------------------------------------------------ LS_Filter_Toeplitz / LS_Filter_Multiple
+# (the clutter filter main.py:169-176 actually calls)
+
+def frequency_shift_oracle(x, fc, Fs, phase_offset=0):
+    """``frequency_shift`` of the reference (passiveRadar/signal_utils.py:24-27).  Note the ramp is
+    ``arange(..., dtype=complex64)``: the phase is evaluated in float32, which the GPU path mirrors."""
+    nn = np.arange(x.shape[0], dtype=np.complex64)
+    return x * np.exp(1j * 2 * np.pi * fc * nn / Fs + 1j * phase_offset)
+
+
+def xcorr_oracle(s1, s2, nlead, nlag):
+    """``xcorr`` of the reference (signal_utils.py:29-32): out[m] = sum_i s1[i] conj(s2[i - m + ...])."""
+    import scipy.signal as signal
+    return signal.correlate(s1, np.pad(s2, (nlag, nlead), mode='constant'), mode='valid')
+
+
+def ls_filter_toeplitz_oracle(refChannel, srvChannel, filterLen, peek=10, return_filter=False):
+    """Follows ``LS_Filter_Toeplitz`` (passiveRadar/clutter_removal.py:109-160): :139 roll by -peek,
+    :142-147 linear (zero-padded) auto/cross correlations, :150 Levinson solve (scipy solve_toeplitz,
+    complex128), :153-155 linear convolution and subtraction.  Returns complex128 like the reference."""
+    from scipy.linalg import solve_toeplitz
+    refChannel = np.asarray(refChannel)
+    srvChannel = np.asarray(srvChannel)
+    if refChannel.shape != srvChannel.shape:
+        raise ValueError(f"Input vectors must have the same length - got {refChannel.shape} and {srvChannel.shape}")
+    shifted = np.roll(refChannel, -1 * peek)
+    ntaps = filterLen + peek
+    acorr = xcorr_oracle(shifted, shifted, 0, ntaps - 1)
+    xc = xcorr_oracle(srvChannel, shifted, 0, ntaps - 1)
+    taps = solve_toeplitz(acorr, xc)
+    clutter = np.convolve(shifted, taps, mode='full')[0:srvChannel.shape[0]]
+    cleaned = srvChannel - clutter
+    return (cleaned, taps) if return_filter else cleaned
+
+
+def ls_filter_multiple_oracle(refChannel, srvChannel, filterLen, sampleRate, dopplerBins=[0]):
+    """Follows ``LS_Filter_Multiple`` (clutter_removal.py:162-187)."""
+    cleaned = srvChannel
+    for doppler in dopplerBins:
+        ref_k = refChannel if doppler == 0 else frequency_shift_oracle(refChannel, doppler, sampleRate)
+        cleaned = ls_filter_toeplitz_oracle(ref_k, cleaned, filterLen)
+    return cleaned

@@ -10,7 +10,38 @@ and a device-resident frame pipeline for streams of CPI frames
 this package never imports the CPU oracle and never falls back to the CPU.
 """
 from .range_doppler_processing import fast_xambg            # noqa: F401
-from .clutter_removal import LS_Filter, NLMS_filter, block_NLMS   # noqa: F401
+from .clutter_removal import (LS_Filter, NLMS_filter, block_NLMS,            # noqa: F401
+                              LS_Filter_Toeplitz, LS_Filter_Multiple)
 
-__all__ = ["fast_xambg", "LS_Filter", "NLMS_filter", "block_NLMS"]
+__all__ = ["fast_xambg", "LS_Filter", "NLMS_filter", "block_NLMS", "LS_Filter_Toeplitz", "LS_Filter_Multiple"]
 __version__ = "0.1.0"
+
+
+def install(reference_package: str = "passiveRadar"):
+    """Swap the hot-path functions of an importable copy of the reference for the GPU ones.
+
+    ``main.py`` binds ``fast_xambg``, ``LS_Filter_Multiple`` and ``NLMS_filter`` with
+    ``from passiveRadar... import ...`` (main.py:10-14); calling ``install()`` before ``main.py`` is
+    imported/run makes those names resolve to this package while config, I/O and the dask graph stay
+    the reference's own code::
+
+        python -c "import passiveradar_b200 as p, runpy; p.install(); runpy.run_path('main.py', run_name='__main__')" --config PRconfig.yaml
+
+    Returns the list of ``module.attribute`` names that were replaced.
+    """
+    import importlib
+    replaced = []
+    table = {
+        "range_doppler_processing": {"fast_xambg": fast_xambg},
+        "clutter_removal": {"LS_Filter": LS_Filter, "NLMS_filter": NLMS_filter,
+                            "LS_Filter_Toeplitz": LS_Filter_Toeplitz, "LS_Filter_Multiple": LS_Filter_Multiple},
+    }
+    for modname, attrs in table.items():
+        mod = importlib.import_module(f"{reference_package}.{modname}")
+        for name, fn in attrs.items():
+            setattr(mod, name, fn)
+            replaced.append(f"{reference_package}.{modname}.{name}")
+        if modname == "clutter_removal" and not hasattr(mod, "block_NLMS"):
+            mod.block_NLMS = block_NLMS
+            replaced.append(f"{reference_package}.{modname}.block_NLMS")
+    return replaced

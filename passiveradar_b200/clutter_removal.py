@@ -87,3 +87,50 @@ def block_NLMS(refChannel, srvChannel, filterLen, mu, peek=10, blockLen=64, init
     if int(blockLen) < 1:
         raise ValueError("blockLen must be >= 1")
     return _nlms(refChannel, srvChannel, filterLen, mu, peek, blockLen, initialTaps, returnFilter, device)
+
+
+def LS_Filter_Toeplitz(refChannel, srvChannel, filterLen, peek=10, return_filter=False, *, device=None):
+    '''Block least squares adaptive filter, Toeplitz (Levinson) formulation -- the variant ``main.py``
+    runs.  Same parameters as the reference (``clutter_removal.py:109-160``); like the reference it
+    returns complex128 (the GPU computes in complex64 with a float64 solve and widens the result).'''
+    refChannel = np.asarray(refChannel)
+    srvChannel = np.asarray(srvChannel)
+    if refChannel.shape != srvChannel.shape:
+        raise ValueError(f'Input vectors must have the same length - got {refChannel.shape} and {srvChannel.shape}')
+    ref = _lib.as_c64(refChannel, "refChannel")
+    srv = _lib.as_c64(srvChannel, "srvChannel")
+    filterLen, peek = int(filterLen), int(peek)
+    n = ref.shape[0]
+    out = np.empty(n, dtype=np.complex64)
+    taps = np.empty(max(filterLen + peek, 0), dtype=np.complex64)
+    lib = _lib.load()
+    dev = _lib.current_device() if device is None else int(device)
+    st = lib.prc_ls_toeplitz_c64(ref.ctypes.data, srv.ctypes.data, n, filterLen, peek, out.ctypes.data,
+                                 taps.ctypes.data, _lib.MEM_HOST, dev, None, 0)
+    _lib.check(st)
+    if return_filter:
+        return out.astype(np.complex128), taps.astype(np.complex128)
+    return out.astype(np.complex128)
+
+
+def LS_Filter_Multiple(refChannel, srvChannel, filterLen, sampleRate, dopplerBins=[0], *, device=None):
+    '''Clutter removal with the Toeplitz least squares filter applied over several Doppler bins
+    (reference ``clutter_removal.py:162-187``; ``main.py:169-176`` calls it with [0, 1, -1, 2, -2]).
+    All bins run back to back on the GPU; the residual never leaves the device between bins.'''
+    refChannel = np.asarray(refChannel)
+    srvChannel = np.asarray(srvChannel)
+    if refChannel.shape != srvChannel.shape:
+        raise ValueError(f'Input vectors must have the same length - got {refChannel.shape} and {srvChannel.shape}')
+    ref = _lib.as_c64(refChannel, "refChannel")
+    srv = _lib.as_c64(srvChannel, "srvChannel")
+    bins = np.ascontiguousarray(list(dopplerBins), dtype=np.float64)
+    if bins.shape[0] == 0:
+        return srvChannel                    # the reference's loop body never runs
+    n = ref.shape[0]
+    out = np.empty(n, dtype=np.complex64)
+    lib = _lib.load()
+    dev = _lib.current_device() if device is None else int(device)
+    st = lib.prc_ls_multiple_c64(ref.ctypes.data, srv.ctypes.data, n, int(filterLen), 10, float(sampleRate),
+                                 bins.ctypes.data, bins.shape[0], out.ctypes.data, None, _lib.MEM_HOST, dev, None, 0)
+    _lib.check(st)
+    return out.astype(np.complex128)

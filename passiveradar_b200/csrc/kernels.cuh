@@ -350,6 +350,7 @@ struct FirParams {
     // plane[q] = out[(q - caf_off) mod n] for q < caf_slen (interleaved re/im, three planes)
     uint16_t* cafs[3];
     long long caf_off, caf_slen;
+    int linear;   // 1: ref[j] = 0 for j < 0 instead of wrapping (np.convolve of LS_Filter_Toeplitz)
 };
 
 __device__ __forceinline__ uint16_t fir_bf16_rn(float v) {
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__((TK * TO > 100) ? 256 : 512) fir_apply_kernel(
         const float2* __restrict__ ref = p.ref;
         constexpr int STAGE_BATCH = 8;          // independent loads in flight per thread
         const int cnt = LO + p.Mpad;
+        const long long lin0 = I0 + p.peek - (p.Mpad - 1);
         for (int base = 0; base < cnt; base += nthr * STAGE_BATCH) {
             float2 v[STAGE_BATCH];
 #pragma unroll
@@ -393,7 +395,8 @@ __global__ void __launch_bounds__((TK * TO > 100) ? 256 : 512) fir_apply_kernel(
                 const int q = base + b * nthr + tid;
                 unsigned idx = start + (unsigned)q;
                 if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }
-                v[b] = (q < cnt) ? ref[idx] : make_float2(0.f, 0.f);
+                const bool ok = q < cnt && (!p.linear || lin0 + q >= 0);
+                v[b] = ok ? ref[idx] : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int b = 0; b < STAGE_BATCH; ++b) {
@@ -801,6 +804,25 @@ __global__ void doppler_dft_kernel(const float2* __restrict__ P, const float2* _
 // ------------------------------------------------------------------------------------------
 // small element-wise helpers
 // ------------------------------------------------------------------------------------------
+// rs[i] = ref[(i + peek) mod n] * exp(i theta_j), j = (i + peek) mod n, theta_j = fl32(fl32(B * j) / Fs):
+// np.roll(frequency_shift(ref, fc, Fs), -peek) with the reference's float32 phase ramp
+// (signal_utils.py:24-27: arange(..., dtype=complex64)); shift == 0 is a plain roll.
+__global__ void shift_roll_kernel(const float2* __restrict__ ref, float2* __restrict__ rs, int n, int peek,
+                                  int shift, float B, float Fs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int j = i + peek;
+    if (j >= n) j %= n;
+    float2 v = ref[j];
+    if (shift) {
+        const float th = __fdiv_rn(__fmul_rn(B, (float)j), Fs);
+        float sn, cs;
+        sincosf(th, &sn, &cs);
+        v = make_float2(__fmaf_rn(v.x, cs, -__fmul_rn(v.y, sn)), __fmaf_rn(v.x, sn, __fmul_rn(v.y, cs)));
+    }
+    rs[i] = v;
+}
+
 __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)in[i];

@@ -36,6 +36,7 @@ struct LagStreamParams {
     long long per_cta;    // samples of the stream per CTA
     int H, G, steps;      // lag groups, sample groups, max TI-steps per group and sub-chunk
     int maxpieces;        // partial rows reserved per block
+    int s_linear;         // 1: s is zero outside [0, n) (LS_Filter_Toeplitz) instead of circular
     float2* partial;      // [prob][nblk][maxpieces][H*TD]
 };
 
@@ -111,10 +112,12 @@ __global__ void __launch_bounds__((TI * TD > 100) ? 256 : 512) lagstream_kernel(
         long long sb = (sc.i0 + dmin) % (long long)n;
         if (sb < 0) sb += n;
         const unsigned start = (unsigned)sb;
+        const long long lin0 = sc.i0 + dmin;
         for (int q = tid; q < Leff + HT; q += nthr) {
             unsigned idx = start + (unsigned)q;
             if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }
-            cp_async8(ss + q, s + idx, true);
+            const bool ok = !p.s_linear || (lin0 + q >= 0 && lin0 + q < (long long)n);
+            cp_async8(ss + q, s + idx, ok);
         }
         cp_async_commit();
     };

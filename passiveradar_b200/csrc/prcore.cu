@@ -114,6 +114,7 @@ struct Ctx {
     bool own_stream = false;
     int nsm = 148;
     std::mutex mu;
+    DBuf rs, clean2;          // LS_Filter_Toeplitz: rolled / frequency-shifted reference, ping-pong output
     DBuf cafplane[6];         // bf16 planes of the tensor-core CAF: x[3], s[3]
     DBuf tcplane[9];          // bf16 planes of the tensor-core path: x[3], s0[3], s1[3]
     DBuf refw, ref, srv, out, clean, partial, win32, win64, dtaps32, dtaps64, lstaps, tw, pbuf, status,
@@ -124,6 +125,8 @@ struct Ctx {
         cudaSetDevice(device);
         for (DBuf& b : tcplane) b.release();
         for (DBuf& b : cafplane) b.release();
+        rs.release();
+        clean2.release();
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
             b->release();
@@ -570,7 +573,8 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
 
 int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek,
               double reg, float2* out, float2* taps_out, const float* win32 = nullptr, bool* refw_ready = nullptr,
-              CafTc* caf = nullptr) {
+              CafTc* caf = nullptr, bool linear = false) {
+    // linear: LS_Filter_Toeplitz semantics -- correlations and FIR treat ref/srv as zero outside [0, n)
     if (refw_ready) *refw_ready = false;
     bool caf_x_done = false;
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
@@ -589,7 +593,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         // ---- tensor-core path: BF16x3 Toeplitz GEMM (toepcorr.cuh)
         const long long nx = (long long)tc_nk * 1024;
         const long long slen = nx + (long long)tc_npass * 128;
-        const bool alias_x = (nx == n);              // x (zero tail) and s0 (circular tail) only differ beyond n
+        const bool alias_x = (nx == n) || linear;    // x (zero tail) and s0 (circular tail) only differ beyond n
         for (int k = 0; k < 9; ++k) {
             if (k < 3 && alias_x) continue;
             TRY(c->tcplane[k].ensure((size_t)(k < 3 ? nx : slen) * 2 * sizeof(uint16_t)));
@@ -605,6 +609,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
             tc::PrepParams pp{};
             pp.sig[0] = ref; pp.sig[1] = srv;
             pp.dmin[0] = 0; pp.dmin[1] = -peek;
+            pp.zero_outside[0] = pp.zero_outside[1] = linear ? 1 : 0;
             for (int k = 0; k < 3; ++k) { pp.plane[0][k] = c->tcplane[3 + k].as<uint16_t>(); pp.plane[1][k] = c->tcplane[6 + k].as<uint16_t>(); }
             pp.win = fold ? win32 : nullptr;
             pp.refw = fold ? c->refw.as<float2>() : nullptr;
@@ -639,7 +644,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         TRY(check_launch("toepcorr_kernel"));
         g.nchunk = tc_npass * tc_ranges;
         g.HT = tc_ht;
-    } else if (g_stream) {
+    } else if (g_stream || linear) {
         StreamGeo sg;
         TRY(choose_stream((int)n, 1, 2, M, c->nsm, &sg));
         TRY(c->partial.ensure((size_t)2 * sg.maxpieces * sg.HT * sizeof(float2)));
@@ -656,6 +661,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         sp.per_cta = sg.per_cta;
         sp.H = sg.H; sp.G = sg.G; sp.steps = sg.steps;
         sp.maxpieces = sg.maxpieces;
+        sp.s_linear = linear ? 1 : 0;
         sp.partial = c->partial.as<float2>();
         {
             ProfScope ps(c, K_LAGCORR_LS);
@@ -717,6 +723,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         caf->planes_ready = true;
     }
     fp.n = (int)n; fp.M = M; fp.peek = peek;
+    fp.linear = linear ? 1 : 0;
     const int mode = g_stream ? 2 : (g_packed ? 1 : 0);
     const int tk = mode == 2 ? kTiles[g_tile].ti : FIR_TK, to = mode == 2 ? kTiles[g_tile].td : FIR_TO;
     fp.Mpad = ceil_div(M, tk) * tk;
@@ -737,6 +744,25 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     if (taps_out)
         CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)M * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
     return PRC_OK;
+}
+
+// LS_Filter_Toeplitz (reference clutter_removal.py:109-160) on the device: roll (and optionally
+// frequency-shift) the reference, then the LS pipeline in linear mode with reg = 0 and all
+// filterLen + peek taps causal on the rolled reference.
+int ls_toeplitz_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek,
+                       bool shift, double fc, double fs, float2* out, float2* taps_out) {
+    if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
+    if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
+        return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
+    TRY(c->rs.ensure((size_t)n * sizeof(float2)));
+    // complex64(1j*2*pi*fc) * complex64(n) / Fs, evaluated like numpy does (see shift_roll_kernel)
+    const float B = (float)(2.0 * 3.14159265358979323846 * fc);
+    {
+        ProfScope ps(c, K_MISC);
+        shift_roll_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(ref, c->rs.as<float2>(), (int)n, peek, shift ? 1 : 0, B, (float)fs);
+    }
+    TRY(check_launch("shift_roll_kernel"));
+    return ls_device(c, c->rs.as<float2>(), srv, n, filter_len + peek, 0, 0.0, out, taps_out, nullptr, nullptr, nullptr, true);
 }
 
 int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek, float mu,
@@ -1079,6 +1105,58 @@ int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_
         if (cleaned_out) CU(cudaMemcpyAsync(cleaned_out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
     }
     TRY(check_ls_status(c, flags));
+    return finish(c, flags);
+}
+
+int prc_ls_toeplitz_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek,
+                        prc_c64* out, prc_c64* taps, int mem_kind, int device, void* stream, unsigned flags) {
+    const double bin0 = 0.0;
+    (void)bin0;
+    return prc_ls_multiple_c64(ref, srv, n, filter_len, peek, 1.0, nullptr, 1, out, taps, mem_kind, device, stream, flags);
+}
+
+int prc_ls_multiple_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek,
+                        double sample_rate, const double* doppler_bins, int nbins, prc_c64* out, prc_c64* taps_last,
+                        int mem_kind, int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (nbins < 1) return fail(PRC_E_INVALID, "nbins=%d invalid", nbins);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const int M = filter_len + peek;
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    float2* dout = reinterpret_cast<float2*>(out);
+    float2* dtaps = reinterpret_cast<float2*>(taps_last);
+    TRY(c->clean.ensure(nb));
+    TRY(c->clean2.ensure(nb));
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->ref.ensure(nb));
+        TRY(c->srv.ensure(nb));
+        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dtaps = nullptr;
+    }
+    // bins are applied one after the other on the running residual (clutter_removal.py:178-187)
+    const float2* cur = dsrv;
+    float2* ping[2] = {c->clean.as<float2>(), c->clean2.as<float2>()};
+    for (int b = 0; b < nbins; ++b) {
+        const double fc = doppler_bins ? doppler_bins[b] : 0.0;
+        const bool last = (b == nbins - 1);
+        float2* dst = (last && mem_kind == PRC_MEM_DEVICE) ? dout : ping[b & 1];
+        TRY(ls_toeplitz_device(c, dref, cur, n, filter_len, peek, fc != 0.0, fc, sample_rate, dst, last ? dtaps : nullptr));
+        if (!(flags & PRC_FLAG_ASYNC)) TRY(check_ls_status(c, 0));      // singular systems are reported per bin
+        cur = dst;
+    }
+    if (mem_kind == PRC_MEM_HOST) {
+        CU(cudaMemcpyAsync(out, cur, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (taps_last) CU(cudaMemcpyAsync(taps_last, c->lstaps.p, (size_t)M * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    }
     return finish(c, flags);
 }
 

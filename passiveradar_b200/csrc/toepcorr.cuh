@@ -481,6 +481,7 @@ struct PrepParams {
     const float2* sig[2];
     int dmin[2];
     int zero_outside[2];    // 1: samples outside [0, n) are zero (x operand); 0: circular (s operand)
+    long long n_valid[2];   // plane entries q >= n_valid are zero (0 = no limit)
     uint16_t* plane[2][3];
     const float* win;       // optional
     float2* refw;           // optional: ref * win for q < n
@@ -514,7 +515,8 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Pr
         if (i >= p.n) i -= p.n;
         if (i >= p.n) i %= p.n;
         const long long lin = q0 + k + p.dmin[sg];           // un-wrapped sample index
-        const bool ok = (q0 + k < p.len) && (!p.zero_outside[sg] || (lin >= 0 && lin < p.n));
+        const bool ok = (q0 + k < p.len) && (!p.zero_outside[sg] || (lin >= 0 && lin < p.n)) &&
+                        (p.n_valid[sg] == 0 || q0 + k < p.n_valid[sg]);
         v[k] = ok ? sig[i] : make_float2(0.f, 0.f);
         w[k] = (sg == 0 && p.refw && q0 + k < p.n) ? p.win[q0 + k] : 1.f;
     }

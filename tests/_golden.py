@@ -58,3 +58,6 @@ XAMBG_C1 = ["xambg_c1_p1", "xambg_c1_p0"]
 LS_SMALL = ["ls_small", "ls_small_peek0", "ls_small_reg0", "ls_mid"]
 LS_C1 = ["ls_c1_p1", "ls_c1_p0"]
 NLMS_ALL = ["nlms_small", "nlms_small_init", "nlms_peek0", "nlms_mid"]
+
+TOEP_ALL = ["toep_small", "toep_small_peek0", "toep_mid"]
+MULTI_ALL = ["multi_small", "multi_main"]

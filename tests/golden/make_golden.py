@@ -38,7 +38,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.environ.get("PR_REFERENCE", "/root/reference"))
 
 from passiveRadar.range_doppler_processing import fast_xambg          # noqa: E402  (the reference)
-from passiveRadar.clutter_removal import LS_Filter, NLMS_filter        # noqa: E402  (the reference)
+from passiveRadar.clutter_removal import LS_Filter, NLMS_filter, LS_Filter_Toeplitz, LS_Filter_Multiple   # noqa: E402  (the reference)
+from passiveRadar.signal_utils import frequency_shift                 # noqa: E402  (the reference)
 from passiveradar_b200 import synth                                    # noqa: E402
 
 
@@ -117,6 +118,38 @@ def ls_case(name, n, filter_len, reg, peek, profile, store_inputs=True, frame=0)
     if store_inputs:
         arrays.update(ref=ref, srv=srv, out=out)
     print(f"{name}: n={n} filterLen={filter_len} reg={reg} peek={peek} {profile} {dt:.2f}s")
+    save(name, **arrays)
+
+
+def toeplitz_case(name, n, filter_len, peek, profile, store_inputs=True, frame=0):
+    ref, srv = synth.make_frame(n, profile, frame)
+    t0 = time.time()
+    out, taps = LS_Filter_Toeplitz(ref, srv, filter_len, peek, True)
+    dt = time.time() - t0
+    idx = subsample_idx(n)
+    arrays = dict(n=n, filter_len=filter_len, peek=peek, profile=profile, frame=frame, taps=taps,
+                  digest=synth.frame_digest(ref, srv), seconds=dt, out_idx=idx, out_sub=out[idx],
+                  out_sum=np.complex128(out.sum()), srv_absmax=np.float64(np.abs(srv).max()))
+    if store_inputs:
+        arrays.update(ref=ref, srv=srv, out=out)
+    print(f"{name}: n={n} filterLen={filter_len} peek={peek} {profile} {dt:.2f}s")
+    save(name, **arrays)
+
+
+def multiple_case(name, n, filter_len, sample_rate, bins, profile, store_inputs=True, frame=0):
+    ref, srv = synth.make_frame(n, profile, frame)
+    t0 = time.time()
+    out = LS_Filter_Multiple(ref, srv, filter_len, sample_rate, list(bins))
+    dt = time.time() - t0
+    idx = subsample_idx(n)
+    arrays = dict(n=n, filter_len=filter_len, sample_rate=sample_rate, bins=np.array(bins, dtype=np.float64),
+                  profile=profile, frame=frame, digest=synth.frame_digest(ref, srv), seconds=dt,
+                  out_idx=idx, out_sub=out[idx], out_sum=np.complex128(out.sum()),
+                  srv_absmax=np.float64(np.abs(srv).max()),
+                  shift_sample=frequency_shift(ref, bins[-1], sample_rate)[idx])
+    if store_inputs:
+        arrays.update(ref=ref, srv=srv, out=out)
+    print(f"{name}: n={n} filterLen={filter_len} Fs={sample_rate} bins={list(bins)} {profile} {dt:.2f}s")
     save(name, **arrays)
 
 
@@ -215,6 +248,20 @@ def main():
         ls_case("ls_c1_p1", n=200_000, filter_len=100, reg=1.0, peek=10, profile="P1", store_inputs=False)
     if want("ls_c1_p0"):
         ls_case("ls_c1_p0", n=200_000, filter_len=100, reg=1.0, peek=10, profile="P0", store_inputs=False)
+
+    # ---- LS_Filter_Toeplitz / LS_Filter_Multiple (what main.py:169-176 calls)
+    if want("toep_small"):
+        toeplitz_case("toep_small", n=4096, filter_len=20, peek=10, profile="P1")
+    if want("toep_small_peek0"):
+        toeplitz_case("toep_small_peek0", n=3000, filter_len=16, peek=0, profile="P0")
+    if want("toep_mid"):
+        toeplitz_case("toep_mid", n=262144, filter_len=175, peek=10, profile="P1", store_inputs=False)
+    if want("multi_small"):
+        multiple_case("multi_small", n=8192, filter_len=24, sample_rate=8192.0, bins=[0, 1, -1], profile="P1")
+    if want("multi_main"):
+        # the shipped PRconfig.yaml: half-CPI chunks of 262144 samples, 175 range cells, IF rate 2.4e6*13/119
+        multiple_case("multi_main", n=262144, filter_len=175, sample_rate=2.4e6 * 13 / 119, bins=[0, 1, -1, 2, -2],
+                      profile="P1", store_inputs=False)
 
     # ---- NLMS_filter
     if want("nlms_small"):

@@ -77,3 +77,28 @@ def test_product_package_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
     assert "oracle" not in {m.split(".")[0] for m in sys.modules if m.startswith("oracle")} or True
+
+
+def test_install_swaps_hot_path_functions_of_a_reference_package(tmp_path, monkeypatch):
+    """install() must make `from passiveRadar.x import f` (main.py:10-14) resolve to the GPU operators."""
+    import sys
+    pkg = tmp_path / "fakeRadar"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    (pkg / "range_doppler_processing.py").write_text("def fast_xambg(*a, **k):\n    return 'cpu'\n")
+    (pkg / "clutter_removal.py").write_text(
+        "def LS_Filter(*a, **k):\n    return 'cpu'\n"
+        "def NLMS_filter(*a, **k):\n    return 'cpu'\n"
+        "def LS_Filter_Toeplitz(*a, **k):\n    return 'cpu'\n"
+        "def LS_Filter_Multiple(*a, **k):\n    return 'cpu'\n"
+        "def GAL_JPE(*a, **k):\n    return 'untouched'\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    replaced = prb.install("fakeRadar")
+    assert "fakeRadar.range_doppler_processing.fast_xambg" in replaced
+    from fakeRadar.clutter_removal import LS_Filter_Multiple, NLMS_filter, GAL_JPE, block_NLMS
+    from fakeRadar.range_doppler_processing import fast_xambg
+    assert fast_xambg is prb.fast_xambg and LS_Filter_Multiple is prb.LS_Filter_Multiple
+    assert NLMS_filter is prb.NLMS_filter and block_NLMS is prb.block_NLMS
+    assert GAL_JPE() == "untouched"
+    for m in [k for k in sys.modules if k.startswith("fakeRadar")]:
+        del sys.modules[m]

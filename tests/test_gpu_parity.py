@@ -317,3 +317,31 @@ def test_frame_pipeline_without_window_and_odd_shape():
     cleaned = prb.LS_Filter(ref, srv, 20, 0.5, 3)
     want = prb.fast_xambg(ref, cleaned, R, F)
     assert G.rel_inf(got, want) <= 2e-6
+
+
+# ------------------------------------------------------------------ LS_Filter_Toeplitz / LS_Filter_Multiple
+@pytest.mark.parametrize("name", G.TOEP_ALL)
+def test_ls_toeplitz_matches_reference_golden(name):
+    g = G.load(name)
+    ref, srv = G.inputs(g)
+    out, taps = prb.LS_Filter_Toeplitz(ref, srv, int(g["filter_len"]), int(g["peek"]), True)
+    assert out.dtype == np.complex128 and taps.dtype == np.complex128        # dtype parity with the reference
+    den = float(g["srv_absmax"])
+    assert G.rel_inf(taps, g["taps"]) <= TOL
+    assert G.rel_inf(out[g["out_idx"]], g["out_sub"], den=den) <= TOL
+
+
+@pytest.mark.parametrize("name", G.MULTI_ALL)
+def test_ls_multiple_matches_reference_golden(name):
+    g = G.load(name)
+    ref, srv = G.inputs(g)
+    out = prb.LS_Filter_Multiple(ref, srv, int(g["filter_len"]), float(g["sample_rate"]), list(g["bins"]))
+    assert out.dtype == np.complex128
+    assert G.rel_inf(out[g["out_idx"]], g["out_sub"], den=float(g["srv_absmax"])) <= TOL
+
+
+def test_ls_multiple_default_bins_equals_toeplitz():
+    ref, srv = synth.make_frame(20000, "P1", frame=8)
+    a = prb.LS_Filter_Multiple(ref, srv, 40, 1000.0)
+    b = prb.LS_Filter_Toeplitz(ref, srv, 40)
+    assert np.array_equal(a, b)

@@ -125,3 +125,23 @@ def test_c_block_nlms_matches_python_definition():
     b, wb = co.block_nlms_oracle(g["ref"], g["srv"], int(g["filter_len"]), float(g["mu"]), int(g["peek"]), 16,
                                  None, True)
     assert G.rel_inf(a, b) < 2e-6 and G.rel_inf(wa, wb) < 2e-5
+
+
+@pytest.mark.parametrize("name", G.TOEP_ALL)
+def test_toeplitz_oracle_matches_reference(name):
+    g = G.load(name)
+    ref, srv = G.inputs(g)
+    out, taps = co.ls_filter_toeplitz_oracle(ref, srv, int(g["filter_len"]), int(g["peek"]), True)
+    assert out.dtype == np.complex128 and taps.dtype == np.complex128
+    assert G.rel_inf(taps, g["taps"]) < 1e-9
+    assert G.rel_inf(out[g["out_idx"]], g["out_sub"], den=float(g["srv_absmax"])) < 1e-9
+
+
+@pytest.mark.parametrize("name", G.MULTI_ALL)
+def test_multiple_oracle_matches_reference(name):
+    g = G.load(name)
+    ref, srv = G.inputs(g)
+    out = co.ls_filter_multiple_oracle(ref, srv, int(g["filter_len"]), float(g["sample_rate"]), list(g["bins"]))
+    assert G.rel_inf(out[g["out_idx"]], g["out_sub"], den=float(g["srv_absmax"])) < 1e-9
+    sh = co.frequency_shift_oracle(ref, float(g["bins"][-1]), float(g["sample_rate"]))
+    assert np.array_equal(sh[g["out_idx"]], g["shift_sample"])
