@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "lagstream.cuh"
 #include "toepcorr.cuh"
+#include "firtc.cuh"
 #include "nlms.cuh"
 
 namespace {
@@ -114,6 +115,7 @@ struct Ctx {
     bool own_stream = false;
     int nsm = 148;
     std::mutex mu;
+    DBuf firb[3];             // Wm^T planes of the tensor-core FIR
     DBuf rs, clean2;          // LS_Filter_Toeplitz: rolled / frequency-shifted reference, ping-pong output
     DBuf cafplane[6];         // bf16 planes of the tensor-core CAF: x[3], s[3]
     DBuf tcplane[9];          // bf16 planes of the tensor-core path: x[3], s0[3], s1[3]
@@ -125,6 +127,7 @@ struct Ctx {
         cudaSetDevice(device);
         for (DBuf& b : tcplane) b.release();
         for (DBuf& b : cafplane) b.release();
+        for (DBuf& b : firb) b.release();
         rs.release();
         clean2.release();
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
@@ -142,6 +145,7 @@ std::atomic<bool> g_attrs_set[64];
 std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
 int g_tune_nchunk = -1, g_tune_g = -1;
 int g_tile = 0;          // measured on B200: 10x10 beats 6x18 / 14x14 (109 vs 117 / 115 us, profiles/r01_tuning.md)
+int g_tc_fir = 1;          // tensor-core path for the clutter FIR (PRC_TC_FIR=0: FP32 fir_apply_kernel)
 int g_tc_caf = 1;          // tensor-core path for the CAF block sums as well (PRC_TC_CAF=0: FP32 lagstream)
 int g_tc = 1;              // tcgen05 Toeplitz-GEMM for the LS correlations (PRC_TC=0: FP32 lagstream kernel)
 int g_stream = 1;          // persistent pipelined lag-correlation kernel (PRC_STREAM=0: one-shot kernel)
@@ -161,6 +165,7 @@ void read_env() {
     if (const char* e = getenv("PRC_STREAM")) g_stream = atoi(e);
     if (const char* e = getenv("PRC_TC")) g_tc = atoi(e);
     if (const char* e = getenv("PRC_TC_CAF")) g_tc_caf = atoi(e);
+    if (const char* e = getenv("PRC_TC_FIR")) g_tc_fir = atoi(e);
     if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
 }
 
@@ -169,6 +174,7 @@ int set_kernel_attrs(int device) {
     const int lim = (int)SMEM_LIMIT;
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::firtc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(tc::toepcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(tc::toepcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -583,6 +589,9 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     const int M = filter_len + peek;
     if (M > 2048) return fail(PRC_E_INVALID, "%d taps exceed the Toeplitz solver's maximum of 2048", M);
     Geo g{};
+    bool use_fir_tc = false;
+    int lead = 0, fir_shift = 0, fir_kv = 0, fir_nblk = 0;
+    long long fir_zoff = 0;
     TRY(c->lstaps.ensure((size_t)M * sizeof(float2)));
     TRY(c->status.ensure(sizeof(int)));
     const int tc_npass = ceil_div(2 * (64 + M), tc::NPASS);
@@ -592,11 +601,27 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     if (g_tc && tc_ranges >= 1 && tc_nk >= 2 * tc_ranges && tc::toep_smem_bytes(tc_ht) <= SMEM_LIMIT) {
         // ---- tensor-core path: BF16x3 Toeplitz GEMM (toepcorr.cuh)
         const long long nx = (long long)tc_nk * 1024;
-        const long long slen = nx + (long long)tc_npass * 128;
+        long long slen = nx + (long long)tc_npass * 128;
         const bool alias_x = (nx == n) || linear;    // x (zero tail) and s0 (circular tail) only differ beyond n
+        // tensor-core FIR geometry (firtc.cuh): the ref planes get a lead-in of `lead` samples so that the
+        // window of output row a starts at plane sample 64 a + lead - pre
+        const int fir_pre = std::max(0, ceil_div(M - 1 - peek, 4) * 4);
+        const int fir_lead = ceil_div(fir_pre, 64) * 64;
+        const int fir_kvp = ceil_div(2 * (64 + peek + fir_pre), 64) * 64;
+        const long long fir_rows = ceil_div(n, 64);
+        const int fir_grid = ceil_div(fir_rows, tc::FIR_ROWS);
+        use_fir_tc = g_tc_fir && fir_grid >= 32 && fir_kvp <= 64 * tc::FIR_MAX_ATOMS && tc::firtc_smem_bytes() <= SMEM_LIMIT;
+        lead = use_fir_tc ? fir_lead : 0;
+        if (use_fir_tc) {
+            fir_shift = peek + fir_pre;
+            fir_kv = fir_kvp;
+            fir_nblk = fir_grid;
+            fir_zoff = 2ll * (fir_lead - fir_pre);
+            slen = std::max(slen, ((long long)fir_grid * tc::FIR_ROWS + tc::FIR_MAX_ATOMS / 2 + 2) * 64);
+        }
         for (int k = 0; k < 9; ++k) {
             if (k < 3 && alias_x) continue;
-            TRY(c->tcplane[k].ensure((size_t)(k < 3 ? nx : slen) * 2 * sizeof(uint16_t)));
+            TRY(c->tcplane[k].ensure((size_t)(k < 3 ? nx : slen + lead) * 2 * sizeof(uint16_t)));
         }
         TRY(c->partial.ensure((size_t)2 * tc_npass * tc_ranges * tc_ht * sizeof(float2)));
         const bool fold = win32 != nullptr && refw_ready != nullptr;
@@ -608,13 +633,13 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
                     ref, (int)n, 0, c->tcplane[0].as<uint16_t>(), c->tcplane[1].as<uint16_t>(), c->tcplane[2].as<uint16_t>(), nx, n);
             tc::PrepParams pp{};
             pp.sig[0] = ref; pp.sig[1] = srv;
-            pp.dmin[0] = 0; pp.dmin[1] = -peek;
+            pp.dmin[0] = -lead; pp.dmin[1] = -peek;         // ref planes start `lead` samples early (FIR window)
             pp.zero_outside[0] = pp.zero_outside[1] = linear ? 1 : 0;
             for (int k = 0; k < 3; ++k) { pp.plane[0][k] = c->tcplane[3 + k].as<uint16_t>(); pp.plane[1][k] = c->tcplane[6 + k].as<uint16_t>(); }
             pp.win = fold ? win32 : nullptr;
             pp.refw = fold ? c->refw.as<float2>() : nullptr;
             pp.n = (int)n;
-            pp.len = slen;
+            pp.len = slen + lead;
             if (fold && caf && caf->on) {          // also emit the CAF x operand (ref * window, shifted by D/2)
                 for (int k = 0; k < 3; ++k) {
                     TRY(c->cafplane[k].ensure((size_t)caf->nx * 2 * sizeof(uint16_t)));
@@ -624,14 +649,14 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
                 pp.caf_nx = caf->nx;
                 caf_x_done = true;
             }
-            tc::tc_prep_kernel<<<dim3(ceil_div(slen, 1024), 2), 256, 0, c->stream>>>(pp);
+            tc::tc_prep_kernel<<<dim3(ceil_div(slen + lead, 1024), 2), 256, 0, c->stream>>>(pp);
         }
         TRY(check_launch("tc_prep_kernel"));
         if (fold) *refw_ready = true;
         tc::ToepParams tp{};
         for (int k = 0; k < 3; ++k) {
-            tp.x[k] = c->tcplane[alias_x ? 3 + k : k].as<uint16_t>();
-            tp.s[0][k] = c->tcplane[3 + k].as<uint16_t>();
+            tp.x[k] = alias_x ? c->tcplane[3 + k].as<uint16_t>() + 2 * lead : c->tcplane[k].as<uint16_t>();
+            tp.s[0][k] = c->tcplane[3 + k].as<uint16_t>() + 2 * lead;
             tp.s[1][k] = c->tcplane[6 + k].as<uint16_t>();
         }
         tp.nk = tc_nk; tp.nlag = M; tp.npass = tc_npass; tp.ranges = tc_ranges; tp.HT = tc_ht;
@@ -711,6 +736,48 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     }
     TRY(check_launch("levinson_kernel"));
 
+    if (use_fir_tc) {
+        for (int k = 0; k < 3; ++k) TRY(c->firb[k].ensure((size_t)tc::FIR_N * fir_kv * sizeof(uint16_t)));
+        {
+            ProfScope ps(c, K_FIR);
+            tc::fir_bmat_kernel<<<ceil_div(tc::FIR_N * fir_kv, 256), 256, 0, c->stream>>>(
+                c->lstaps.as<float2>(), M, fir_shift, fir_kv, c->firb[0].as<uint16_t>(), c->firb[1].as<uint16_t>(), c->firb[2].as<uint16_t>());
+            tc::FirTcParams ft{};
+            for (int k = 0; k < 3; ++k) { ft.z[k] = c->tcplane[3 + k].as<uint16_t>(); ft.b[k] = c->firb[k].as<uint16_t>(); }
+            ft.zoff = fir_zoff;
+            ft.kvp = fir_kv;
+            ft.srv = srv; ft.out = out; ft.n = (int)n;
+            if (caf && caf->on && caf_x_done) {
+                for (int k = 0; k < 3; ++k) {
+                    TRY(c->cafplane[3 + k].ensure((size_t)caf->slen * 2 * sizeof(uint16_t)));
+                    ft.cafs[k] = c->cafplane[3 + k].as<uint16_t>();
+                }
+                ft.caf_off = caf->D / 2;
+                ft.caf_slen = caf->slen;
+                caf->planes_ready = true;
+            }
+            static long long* dbg = nullptr;
+            if (getenv("PRC_FIR_DEBUG")) {
+                if (!dbg) cudaMalloc(&dbg, 256);
+                cudaMemsetAsync(dbg, 0, 256, c->stream);
+                ft.debug_clk = dbg;
+            }
+            tc::firtc_kernel<<<fir_nblk, tc::FIR_THREADS, tc::firtc_smem_bytes(), c->stream>>>(ft);
+            if (ft.debug_clk) {
+                long long h[32];
+                cudaMemcpyAsync(h, dbg, 256, cudaMemcpyDeviceToHost, c->stream);
+                cudaStreamSynchronize(c->stream);
+                fprintf(stderr, "[firtc] grid=%d kvp=%d: last MMA commit %lld, tmem_full seen %lld, all done %lld cycles; full[kc] at",
+                        fir_nblk, fir_kv, h[1] - h[0], h[2] - h[0], h[3] - h[0]);
+                for (int k = 0; k < 12; ++k) fprintf(stderr, " %lld", h[4 + k] - h[0]);
+                fprintf(stderr, "; slowest CTA %lld cycles, first start -> last end %lld ns\n", h[20], h[22] - (long long)~(unsigned long long)h[21]);
+            }
+        }
+        TRY(check_launch("firtc_kernel"));
+        if (taps_out)
+            CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)M * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+        return PRC_OK;
+    }
     FirParams fp{};
     fp.ref = ref; fp.srv = srv; fp.taps = c->lstaps.as<float2>(); fp.out = out;
     if (caf && caf->on && caf_x_done) {           // the FIR writes the CAF s operand (cleaned channel) as well

@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Pr
         const bool ok = (q0 + k < p.len) && (!p.zero_outside[sg] || (lin >= 0 && lin < p.n)) &&
                         (p.n_valid[sg] == 0 || q0 + k < p.n_valid[sg]);
         v[k] = ok ? sig[i] : make_float2(0.f, 0.f);
-        w[k] = (sg == 0 && p.refw && q0 + k < p.n) ? p.win[q0 + k] : 1.f;
+        w[k] = (sg == 0 && p.refw && lin >= 0 && lin < p.n) ? p.win[lin] : 1.f;
     }
     uint32_t o[3][4];
 #pragma unroll
@@ -545,28 +545,30 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Pr
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl) reinterpret_cast<uint32_t*>(p.plane[sg][pl])[q0 + k] = o[pl][k];
     }
+    // signal 0 may carry a lead-in (dmin < 0): its sample index is lin = q + dmin
+    const long long lin0 = q0 + p.dmin[0];
     if (sg == 0 && p.refw) {
         for (int k = 0; k < 4; ++k)
-            if (q0 + k < p.n) p.refw[q0 + k] = make_float2(v[k].x * w[k], v[k].y * w[k]);
+            if (lin0 + k >= 0 && lin0 + k < p.n && q0 + k < p.len) p.refw[lin0 + k] = make_float2(v[k].x * w[k], v[k].y * w[k]);
     }
-    if (sg == 0 && p.cafx[0]) {
+    if (sg == 0 && p.cafx[0] && lin0 >= 0) {
         uint32_t c[3][4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             uint16_t br[3], bi[3];
-            const bool in = q0 + k < p.n;
+            const bool in = lin0 + k < p.n && q0 + k < p.len;
             bf16_split3(in ? v[k].x * w[k] : 0.f, br);
             bf16_split3(in ? v[k].y * w[k] : 0.f, bi);
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl) c[pl][k] = (uint32_t)br[pl] | ((uint32_t)bi[pl] << 16);
         }
-        const long long t0 = q0 + p.caf_off;
+        const long long t0 = lin0 + p.caf_off;
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) {
             uint32_t* dst = reinterpret_cast<uint32_t*>(p.cafx[pl]);
-            if (q0 < p.n && t0 + 3 < p.caf_nx) reinterpret_cast<uint4*>(dst)[t0 / 4] = make_uint4(c[pl][0], c[pl][1], c[pl][2], c[pl][3]);
-            else for (int k = 0; k < 4; ++k) if (q0 + k < p.n && t0 + k < p.caf_nx) dst[t0 + k] = c[pl][k];
-            if (q0 < p.caf_off) for (int k = 0; k < 4; ++k) if (q0 + k < p.caf_off && q0 + k < p.caf_nx) dst[q0 + k] = 0u;   // zero lead-in
+            if (lin0 + 3 < p.n && t0 + 3 < p.caf_nx) reinterpret_cast<uint4*>(dst)[t0 / 4] = make_uint4(c[pl][0], c[pl][1], c[pl][2], c[pl][3]);
+            else for (int k = 0; k < 4; ++k) if (lin0 + k < p.n && t0 + k < p.caf_nx) dst[t0 + k] = c[pl][k];
+            if (lin0 < p.caf_off) for (int k = 0; k < 4; ++k) if (lin0 + k < p.caf_off && lin0 + k < p.caf_nx) dst[lin0 + k] = 0u;   // zero lead-in
         }
     }
 }
