@@ -75,9 +75,30 @@ def kernel_alg_bytes(cfg):
 
 
 def kernel_alg_flops(cfg):
+    """Algorithmic flops per launch: direct-form complex MACs (8 flop each), SURVEY.md 8d."""
     n, F, R = cfg["n"], cfg["F"], cfg["R"]
     M = cfg["filter_len"] + cfg["peek"]
     return {"lagcorr_ls": 2 * 8 * n * M, "fir_apply": 8 * n * M, "lagcorr_caf": 8 * n * (R + 1)}
+
+
+def kernel_issued_flops(cfg):
+    """BF16 tensor-core flops the tcgen05 kernels actually issue per launch:
+    every product is evaluated as 6 BF16 MMAs (three-way split), the Toeplitz GEMMs compute a
+    128 x 256 tile per 64-lag group (toepcorr.cuh) and the FIR a 128 x 128 tile per 64 samples over
+    K = 2*(64 + M) padded to 64 (firtc.cuh).  Mirrors the geometry chosen in prcore.cu."""
+    n, F, R = cfg["n"], cfg["F"], cfg["R"]
+    M = cfg["filter_len"] + cfg["peek"]
+    ceil = lambda a, b: -(-a // b)
+    mma_toep = 2 * 128 * 256 * 16
+    nk = ceil(n, 1024)
+    out = {"lagcorr_ls": 2 * ceil(2 * (64 + M), 256) * nk * 6 * mma_toep}
+    D = n // F
+    if D % 1024 == 0:
+        out["lagcorr_caf"] = F * ceil(2 * (64 + R + 1), 256) * (D // 1024) * 6 * mma_toep
+    pre = max(0, ceil(M - 1 - cfg["peek"], 4) * 4)
+    kvp = ceil(2 * (64 + cfg["peek"] + pre), 64) * 64
+    out["fir_apply"] = ceil(ceil(n, 64), 128) * (kvp // 16) * 6 * (2 * 128 * 128 * 16)
+    return out
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -363,13 +384,29 @@ def run_b200(args, cfg, rank, world, local_rank):
         if args.config == "c2" and os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get(dom)      # dram read+write bytes per launch from the ncu --set full capture
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": round(ach / peaks["hbm_gbs"], 5), "traffic": traffic, "peak_source": peaks["source"],
-                    "avg_launch_us": per_kernel[dom]["avg_us"],
-                    "fp32_TFLOPs": per_kernel[dom]["alg_TFLOPs"],
-                    "fp32_frac_of_peak": round(per_kernel[dom]["alg_TFLOPs"] / (148 * 128 * 2 * 1.965e-3), 4),
-                    "note": "direct-form lag correlation: 8*N*M flop per 16*N bytes (145+ flop/B) => FP32-pipe bound, not HBM bound; see DESIGN.md section 4",
-                    "frame_GBps": round(bytes_frame(n, F, R) * value / world / 1e9, 2)}
+        tensor = os.environ.get("PRC_TC", "1") != "0" and dom in ("lagcorr_ls", "lagcorr_caf", "fir_apply")
+        fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e-6          # FFMA: 128 lanes x 2 flop x SMs x clock
+        common = {"traffic": traffic, "avg_launch_us": per_kernel[dom]["avg_us"],
+                  "alg_GBps": ach, "hbm_peak_GBps": peaks["hbm_gbs"],
+                  "alg_TFLOPs": per_kernel[dom]["alg_TFLOPs"], "fp32_pipe_peak_TFLOPs": round(fp32_peak, 1),
+                  "frame_GBps": round(bytes_frame(n, F, R) * value / world / 1e9, 2),
+                  "peak_source": peaks["source"]}
+        if tensor:
+            issued = kernel_issued_flops(cfg).get(dom)
+            issued_tf = issued / (per_kernel[dom]["avg_us"] * 1e-6) / 1e12 if issued else None
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": per_kernel[dom]["alg_TFLOPs"],
+                        "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": round(per_kernel[dom]["alg_TFLOPs"] / peaks["bf16_tflops_sustained"], 5),
+                        "issued_bf16_TFLOPs": round(issued_tf, 1) if issued_tf else None,
+                        "issued_frac": round(issued_tf / peaks["bf16_tflops_sustained"], 4) if issued_tf else None,
+                        "note": "algorithmic flops = direct-form complex MACs (8 flop); the kernel issues 6 BF16 MMAs per "
+                                "product (fp32-accurate three-way split) on Toeplitz-expanded tiles, so `issued` is what the "
+                                "tensor pipe actually sustains; the same algorithmic work on the FP32 pipe is capped at "
+                                "fp32_pipe_peak_TFLOPs. 145+ flop/B: not HBM bound (DESIGN.md section 4)", **common}
+        else:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(ach / peaks["hbm_gbs"], 5),
+                        "fp32_frac_of_peak": round(per_kernel[dom]["alg_TFLOPs"] / fp32_peak, 4), **common}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -410,8 +447,12 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "source": "MEASURED_PEAKS.json (measured copy bandwidth)"}
-    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops", 1718.7)),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1453.0))),
+                "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)),
+                "source": "MEASURED_PEAKS.json (measured copy bandwidth / sustained cuBLAS bf16, kernel timed inside a long step)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1700.0, "bf16_tflops_sustained": 1450.0, "sm_max_mhz": 1965.0,
+            "source": "fallback (B200_PROFILING.md)"}
 
 
 def main():
