@@ -53,6 +53,7 @@ typedef struct prc_c64 { float re, im; } prc_c64;
 /* flags */
 #define PRC_FLAG_ASYNC        1u   /* do not synchronise `stream` before returning */
 #define PRC_FLAG_WINDOW_F32   2u   /* `window` points at float, not double */
+#define PRC_FLAG_ABS_C64      4u   /* prc_cfar2d_f32: `x` is a complex64 map, |x| is used */
 
 /* ---- lifecycle / diagnostics ------------------------------------------------ */
 int         prc_version(void);
@@ -149,6 +150,53 @@ int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n,
                   int range_bins, int freq_bins, const void* window,
                   prc_c64* out_map, prc_c64* taps_out, prc_c64* cleaned_out,
                   int mem_kind, int device, void* stream, unsigned flags);
+
+/* ---- direct (time-domain) cross-ambiguity function ------------------------------------------------
+ * Replaces direct_xambg(), reference passiveRadar/range_doppler_processing.py:93-124: for Doppler bin f
+ * the reference channel is frequency-shifted by (f - freq_bins/2) / CPI Hz (signal_utils.py:24-27,
+ * float32 phase ramp and complex64 exponential as in the reference) and LINEARLY cross-correlated
+ * with srv (xcorr(ref_shifted, srv, range_bins, 0), signal_utils.py:29-32).  out: freq_bins x
+ * (range_bins + 1) complex64, column k <-> delay range_bins - k (same orientation as prc_xambg_c64).
+ */
+int prc_direct_xambg_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int range_bins, int freq_bins,
+                         double sample_rate, prc_c64* out, int mem_kind, int device, void* stream, unsigned flags);
+
+/* ---- front end: the chain main.py:105-166 runs on every input chunk before the clutter filter -------
+ * in_kind : PRC_IQ_C64 (n complex64 samples), PRC_IQ_I8 / PRC_IQ_I16 (2n interleaved I,Q integers:
+ *           deinterleave_IQ(), reference passiveRadar/signal_utils.py:19-22)
+ * mode    : PRC_MIX_NONE, or frequency_shift(x, fc, fs, phase_offset) (signal_utils.py:24-27) with the
+ *           reference's float32 phase ramp; PRC_MIX_C64 = phase_offset is a Python scalar (complex64
+ *           arithmetic throughout), PRC_MIX_C128 = phase_offset is a NumPy float64 (main.py:127-130;
+ *           the exponential is then evaluated in float64).  Results are complex64 either way.
+ * prc_frontend_c64 additionally applies resample() = scipy.signal.resample_poly(x, up, down,
+ * padtype='line') (signal_utils.py:15-17) in the same pass: h = the nh = 2*half_len+1 low-pass taps
+ * ALREADY multiplied by up (what resample_poly hands to upfirdn; host doubles, designed by the caller
+ * with scipy.signal.firwin exactly as resample_poly does).  out receives prc_resample_out_len() samples.
+ */
+#define PRC_IQ_C64   0
+#define PRC_IQ_I8    1
+#define PRC_IQ_I16   2
+#define PRC_MIX_NONE 0
+#define PRC_MIX_C64  1
+#define PRC_MIX_C128 2
+#define PRC_MIX_F64  3   /* fc was a NumPy float64 scalar: the phase ramp is evaluated in float64 */
+#define PRC_MIX_FS64 4   /* only fs was a NumPy float64 scalar: float32 product, float64 division */
+int prc_iq_mix_c64(const void* in, int in_kind, int64_t n, int mode, double fc, double fs, double phase_offset,
+                   prc_c64* out, int mem_kind, int device, void* stream, unsigned flags);
+int prc_resample_out_len(int64_t n_in, int up, int down, int nh, int64_t* n_out);
+int prc_frontend_c64(const void* in, int in_kind, int64_t n, int mode, double fc, double fs, double phase_offset,
+                     int up, int down, const double* h, int nh, prc_c64* out, int64_t out_capacity,
+                     int mem_kind, int device, void* stream, unsigned flags);
+
+/* ---- CFAR detector ---------------------------------------------------------------------------------
+ * Replaces CFAR_2D(X, fw, gw, thresh), reference passiveRadar/target_detection.py:683-703: X / mean|X|
+ * divided by the wrapped 2-D box average (fw x fw window minus the guard hole) + 1e-10.
+ * x: rows x cols float32 (or complex64 with PRC_FLAG_ABS_C64: the magnitude is taken on the device, so
+ * a map can go from prc_xambg_c64 to the detector without leaving HBM).  cr_out (float32) and/or
+ * det_out (uint8, cr > *thresh) are written; thresh may be NULL when det_out is NULL.
+ */
+int prc_cfar2d_f32(const void* x, int rows, int cols, int fw, int gw, const float* thresh, float* cr_out,
+                   uint8_t* det_out, int mem_kind, int device, void* stream, unsigned flags);
 
 #ifdef __cplusplus
 }

@@ -9,11 +9,14 @@ and a device-resident frame pipeline for streams of CPI frames
 ``libprcore.so`` (hand-written CUDA, C ABI in ``include/prcore.h``); importing
 this package never imports the CPU oracle and never falls back to the CPU.
 """
-from .range_doppler_processing import fast_xambg            # noqa: F401
+from .range_doppler_processing import fast_xambg, direct_xambg            # noqa: F401
 from .clutter_removal import (LS_Filter, NLMS_filter, block_NLMS,            # noqa: F401
                               LS_Filter_Toeplitz, LS_Filter_Multiple)
+from .signal_utils import deinterleave_IQ, frequency_shift, resample, frontend            # noqa: F401
+from .target_detection import CFAR_2D            # noqa: F401
 
-__all__ = ["fast_xambg", "LS_Filter", "NLMS_filter", "block_NLMS", "LS_Filter_Toeplitz", "LS_Filter_Multiple"]
+__all__ = ["fast_xambg", "direct_xambg", "LS_Filter", "NLMS_filter", "block_NLMS", "LS_Filter_Toeplitz",
+           "LS_Filter_Multiple", "deinterleave_IQ", "frequency_shift", "resample", "frontend", "CFAR_2D"]
 __version__ = "0.1.0"
 
 
@@ -32,12 +35,19 @@ def install(reference_package: str = "passiveRadar"):
     import importlib
     replaced = []
     table = {
-        "range_doppler_processing": {"fast_xambg": fast_xambg},
+        "range_doppler_processing": {"fast_xambg": fast_xambg, "direct_xambg": direct_xambg},
+        "signal_utils": {"deinterleave_IQ": deinterleave_IQ, "frequency_shift": frequency_shift, "resample": resample},
+        "target_detection": {"CFAR_2D": CFAR_2D},
         "clutter_removal": {"LS_Filter": LS_Filter, "NLMS_filter": NLMS_filter,
                             "LS_Filter_Toeplitz": LS_Filter_Toeplitz, "LS_Filter_Multiple": LS_Filter_Multiple},
     }
     for modname, attrs in table.items():
-        mod = importlib.import_module(f"{reference_package}.{modname}")
+        try:
+            mod = importlib.import_module(f"{reference_package}.{modname}")
+        except Exception:          # e.g. the reference's target_detection needs np.float (NumPy < 1.24)
+            if modname in ("range_doppler_processing", "clutter_removal"):
+                raise
+            continue
         for name, fn in attrs.items():
             setattr(mod, name, fn)
             replaced.append(f"{reference_package}.{modname}.{name}")

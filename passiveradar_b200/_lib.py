@@ -25,6 +25,9 @@ MEM_HOST = 0
 MEM_DEVICE = 1
 FLAG_ASYNC = 1
 FLAG_WINDOW_F32 = 2
+FLAG_ABS_C64 = 4
+IQ_C64, IQ_I8, IQ_I16 = 0, 1, 2
+MIX_NONE, MIX_C64, MIX_C128, MIX_F64, MIX_FS64 = 0, 1, 2, 3, 4
 
 # every symbol include/prcore.h declares: name -> (restype, argtypes)
 _c64p = C.c_void_p
@@ -57,6 +60,16 @@ SIGNATURES = {
                                _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_frame_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                 C.c_void_p, _c64p, _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_direct_xambg_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int, C.c_double, _c64p,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_iq_mix_c64": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                 _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_resample_out_len": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    "prc_frontend_c64": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_int, _c64p, C.c_int64,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_cfar2d_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
 }
 
 _lib = None

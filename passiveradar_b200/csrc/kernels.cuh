@@ -804,18 +804,19 @@ __global__ void doppler_dft_kernel(const float2* __restrict__ P, const float2* _
 // ------------------------------------------------------------------------------------------
 // small element-wise helpers
 // ------------------------------------------------------------------------------------------
-// rs[i] = ref[(i + peek) mod n] * exp(i theta_j), j = (i + peek) mod n, theta_j = fl32(fl32(B * j) / Fs):
+// rs[i] = ref[(i + peek) mod n] * exp(i theta_j), j = (i + peek) mod n, theta_j = fl32(fl32(B * j) * fl32(1/Fs))
+// (numpy divides a complex64 array by a real scalar as a multiplication by the float32 reciprocal):
 // np.roll(frequency_shift(ref, fc, Fs), -peek) with the reference's float32 phase ramp
 // (signal_utils.py:24-27: arange(..., dtype=complex64)); shift == 0 is a plain roll.
 __global__ void shift_roll_kernel(const float2* __restrict__ ref, float2* __restrict__ rs, int n, int peek,
-                                  int shift, float B, float Fs) {
+                                  int shift, float B, float rFs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int j = i + peek;
     if (j >= n) j %= n;
     float2 v = ref[j];
     if (shift) {
-        const float th = __fdiv_rn(__fmul_rn(B, (float)j), Fs);
+        const float th = __fmul_rn(__fmul_rn(B, (float)j), rFs);
         float sn, cs;
         sincosf(th, &sn, &cs);
         v = make_float2(__fmaf_rn(v.x, cs, -__fmul_rn(v.y, sn)), __fmaf_rn(v.x, sn, __fmul_rn(v.y, cs)));

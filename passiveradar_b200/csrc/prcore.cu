@@ -25,6 +25,8 @@
 #include "lagstream.cuh"
 #include "toepcorr.cuh"
 #include "firtc.cuh"
+#include "frontend.cuh"
+#include "detect.cuh"
 #include "nlms.cuh"
 
 namespace {
@@ -116,6 +118,8 @@ struct Ctx {
     int nsm = 148;
     std::mutex mu;
     DBuf firb[3];             // Wm^T planes of the tensor-core FIR
+    DBuf fe_in, fe_mid, fe_out, fe_hp, fe_ends;    // front end: raw IQ, mixed, resampled, polyphase taps, end points
+    DBuf cf_in, cf_cr, cf_det, cf_part;            // CFAR_2D
     DBuf rs, clean2;          // LS_Filter_Toeplitz: rolled / frequency-shifted reference, ping-pong output
     DBuf cafplane[6];         // bf16 planes of the tensor-core CAF: x[3], s[3]
     DBuf tcplane[9];          // bf16 planes of the tensor-core path: x[3], s0[3], s1[3]
@@ -130,6 +134,7 @@ struct Ctx {
         for (DBuf& b : firb) b.release();
         rs.release();
         clean2.release();
+        for (DBuf* b : {&fe_in, &fe_mid, &fe_out, &fe_hp, &fe_ends, &cf_in, &cf_cr, &cf_det, &cf_part}) b->release();
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
             b->release();
@@ -826,10 +831,156 @@ int ls_toeplitz_device(Ctx* c, const float2* ref, const float2* srv, long long n
     const float B = (float)(2.0 * 3.14159265358979323846 * fc);
     {
         ProfScope ps(c, K_MISC);
-        shift_roll_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(ref, c->rs.as<float2>(), (int)n, peek, shift ? 1 : 0, B, (float)fs);
+        shift_roll_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(ref, c->rs.as<float2>(), (int)n, peek, shift ? 1 : 0, B, 1.0f / (float)fs);
     }
     TRY(check_launch("shift_roll_kernel"));
     return ls_device(c, c->rs.as<float2>(), srv, n, filter_len + peek, 0, 0.0, out, taps_out, nullptr, nullptr, nullptr, true);
+}
+
+// ---- front end (frontend.cuh) -------------------------------------------------------------------
+size_t iq_bytes(int kind, long long n) {
+    return (size_t)n * (kind == IQ_I8 ? 2 : kind == IQ_I16 ? 4 : 8);
+}
+
+MixParams make_mix(const void* in, int kind, long long n, int mode, double fc, double fs, double po) {
+    MixParams m{};
+    m.in = in; m.kind = kind; m.n = n; m.mode = mode;
+    m.B = (float)(2.0 * 3.14159265358979323846 * fc);
+    m.rFs = 1.0f / (float)fs;
+    m.po = po;
+    m.B64 = 2.0 * 3.14159265358979323846 * fc;
+    m.rFs64 = 1.0 / fs;
+    return m;
+}
+
+int mix_device(Ctx* c, const MixParams& m, float2* out) {
+    ProfScope ps(c, K_MISC);
+    iq_mix_kernel<<<ceil_div(m.n, 256), 256, 0, c->stream>>>(m, out);
+    return check_launch("iq_mix_kernel");
+}
+
+// scipy.signal.resample_poly(x, up, down, padtype='line') geometry (scipy/signal/_signaltools.py, resample_poly)
+struct ResampleGeo { int up, down, n_pre_pad, n_pre_remove, tpp; long long n_out; };
+
+int resample_geo(long long n_in, int up, int down, int nh, ResampleGeo* g) {
+    if (up < 1 || down < 1) return fail(PRC_E_INVALID, "up and down must be >= 1");
+    if (nh < 1 || (nh & 1) == 0) return fail(PRC_E_INVALID, "nh=%d: the filter must have 2*half_len+1 taps", nh);
+    long long a = up, b = down;
+    while (b) { const long long t = a % b; a = b; b = t; }
+    up /= (int)a; down /= (int)a;
+    const int half_len = (nh - 1) / 2;
+    g->up = up; g->down = down;
+    g->n_pre_pad = down - half_len % down;
+    g->n_pre_remove = (half_len + g->n_pre_pad) / down;
+    g->n_out = (n_in * up + down - 1) / down;
+    g->tpp = ceil_div(g->n_pre_pad + nh, up);
+    return PRC_OK;
+}
+
+// h: host doubles (already multiplied by `up`, as resample_poly does before upfirdn)
+int resample_device(Ctx* c, const MixParams& mix, int up_in, int down_in, const double* h, int nh, float2* out,
+                    long long* n_out) {
+    ResampleGeo g;
+    TRY(resample_geo(mix.n, up_in, down_in, nh, &g));
+    if (mix.n < 1) return fail(PRC_E_INVALID, "n=%lld invalid", mix.n);
+    if (n_out) *n_out = g.n_out;
+    if (g.up == 1 && g.down == 1) {           // resample_poly returns a copy
+        return mix_device(c, mix, out);
+    }
+    ResampleParams rp{};
+    rp.mix = mix;
+    rp.up = g.up; rp.down = g.down; rp.nh = nh;
+    rp.n_pre_pad = g.n_pre_pad; rp.n_pre_remove = g.n_pre_remove; rp.tpp = g.tpp;
+    rp.n_out = g.n_out;
+    rp.span = (int)(((long long)(RS_THREADS - 1) * g.down) / g.up) + 2 + g.tpp;
+    const size_t hp_bytes = (((size_t)g.up * g.tpp * 4 + 15) & ~(size_t)15);
+    const size_t smem = hp_bytes + (size_t)rp.span * sizeof(float2);
+    if (smem > SMEM_LIMIT)
+        return fail(PRC_E_INVALID, "resample %d/%d with %d taps needs %zu bytes of shared memory per CTA", g.up, g.down, nh, smem);
+    // polyphase table on the host (nh ~ 2.4k taps), staged through the stream
+    std::vector<float> hp((size_t)g.up * g.tpp, 0.f);
+    for (int k = g.n_pre_pad; k < g.n_pre_pad + nh; ++k) hp[(size_t)(k % g.up) * g.tpp + k / g.up] = (float)h[k - g.n_pre_pad];
+    TRY(c->fe_hp.ensure(hp.size() * sizeof(float)));
+    TRY(c->fe_ends.ensure(2 * sizeof(float2)));
+    CU(cudaMemcpyAsync(c->fe_hp.p, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));     // hp is a stack-lifetime host buffer
+    rp.hp = c->fe_hp.as<float>();
+    rp.ends = c->fe_ends.as<float2>();
+    static std::atomic<bool> attr_set[64];
+    if (!attr_set[c->device].exchange(true))
+        CU(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    {
+        ProfScope ps(c, K_MISC);
+        resample_ends_kernel<<<1, 32, 0, c->stream>>>(mix, c->fe_ends.as<float2>());
+        resample_kernel<<<ceil_div(g.n_out, RS_THREADS), RS_THREADS, smem, c->stream>>>(rp, out);
+    }
+    return check_launch("resample_kernel");
+}
+
+// ---- CFAR_2D (detect.cuh) -----------------------------------------------------------------------
+int cfar_device(Ctx* c, const void* x, bool is_complex, int rows, int cols, int fw, int gw, const float* thresh,
+                float* cr, uint8_t* det) {
+    if (rows < 1 || cols < 1) return fail(PRC_E_INVALID, "rows=%d cols=%d invalid", rows, cols);
+    if (fw < 1 || fw > CFAR_MAX_FW) return fail(PRC_E_INVALID, "fw=%d outside [1, %d]", fw, CFAR_MAX_FW);
+    if (gw < 0 || fw * fw - gw * gw == 0) return fail(PRC_E_INVALID, "fw=%d gw=%d: fw^2 - gw^2 must not be 0", fw, gw);
+    TRY(c->cf_part.ensure(CFAR_MEAN_CTAS * sizeof(double)));
+    CfarParams p{};
+    p.x = x; p.is_complex = is_complex ? 1 : 0; p.rows = rows; p.cols = cols;
+    p.fw = fw;
+    // python: e1 = (fw - gw) // 2 (floor), e2 = fw - e1 + 1; slices clip to [0, fw]
+    int e1 = (fw - gw) >= 0 ? (fw - gw) / 2 : -((gw - fw + 1) / 2);
+    int e2 = fw - e1 + 1;
+    if (e1 < 0) e1 = std::max(0, e1 + fw);     // negative slice start counts from the end
+    p.e1 = std::min(e1, fw); p.e2 = std::min(std::max(e2, 0), fw);
+    p.c = (fw - 1) / 2;
+    p.scale = (float)(1.0 / ((double)fw * fw - (double)gw * gw));
+    p.has_thresh = thresh ? 1 : 0;
+    p.thresh = thresh ? *thresh : 0.f;
+    p.partial = c->cf_part.as<double>();
+    p.cr = cr; p.det = det;
+    ProfScope ps(c, K_MISC);
+    cfar_abssum_kernel<<<CFAR_MEAN_CTAS, 256, 0, c->stream>>>(p, c->cf_part.as<double>());
+    const size_t smem = (size_t)(CFAR_TX + fw - 1) * (CFAR_TY + fw - 1) * sizeof(float);
+    cfar2d_kernel<<<dim3(ceil_div(cols, CFAR_TX), ceil_div(rows, CFAR_TY)), dim3(CFAR_TX, CFAR_TY), smem, c->stream>>>(p);
+    return check_launch("cfar2d_kernel");
+}
+
+// ---- direct_xambg (reference range_doppler_processing.py:93-124) ---------------------------------
+// row f: xcorr(frequency_shift(ref, (f - F/2)/CPI, Fs), srv, R, 0): a LINEAR lag correlation of the
+// frequency-shifted reference (float32 phase ramp, complex64 exp -- as the reference) with srv.
+int direct_xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int R, int F, double fs, float2* out) {
+    if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
+    if (R < 0 || F < 1) return fail(PRC_E_INVALID, "range_bins=%d freq_bins=%d invalid", R, F);
+    if (!(fs > 0)) return fail(PRC_E_INVALID, "sample_rate must be > 0");
+    TRY(c->rs.ensure((size_t)n * sizeof(float2)));
+    StreamGeo sg;
+    TRY(choose_stream((int)n, 1, 1, R + 1, c->nsm, &sg));
+    TRY(c->partial.ensure((size_t)sg.maxpieces * sg.HT * sizeof(float2)));
+    const double cpi = (double)n / fs;
+    for (int f = 0; f < F; ++f) {
+        const double df = ((double)f - 0.5 * (double)F) / cpi;
+        const MixParams m = make_mix(ref, IQ_C64, n, MIX_C64, df, fs, 0.0);
+        TRY(mix_device(c, m, c->rs.as<float2>()));
+        LagStreamParams sp{};
+        sp.x = c->rs.as<float2>();
+        sp.s[0] = srv; sp.s[1] = srv;
+        sp.dmin[0] = 0; sp.dmin[1] = 0;
+        sp.n = (int)n;
+        sp.blk_first_lo = 0; sp.blk_stride = 0; sp.blk_len = (int)n; sp.nblk = 1;
+        sp.total = sg.total; sp.per_cta = sg.per_cta;
+        sp.H = sg.H; sp.G = sg.G; sp.steps = sg.steps;
+        sp.maxpieces = sg.maxpieces;
+        sp.s_linear = 1;
+        sp.partial = c->partial.as<float2>();
+        {
+            ProfScope ps(c, K_LAGCORR_CAF);
+            launch_lagstream(dim3(sg.ncta, 1), sg.threads, sg.smem, c->stream, sp);
+            piece_sum_kernel<<<ceil_div(R + 1, 128), 128, 0, c->stream>>>(c->partial.as<float2>(), sg.maxpieces, sg.HT, R,
+                                                                     out + (size_t)f * (R + 1));
+        }
+        TRY(check_launch("lagstream_kernel(direct_xambg)"));
+    }
+    return PRC_OK;
 }
 
 int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek, float mu,
@@ -1224,6 +1375,128 @@ int prc_ls_multiple_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int f
         CU(cudaMemcpyAsync(out, cur, nb, cudaMemcpyDeviceToHost, c->stream));
         if (taps_last) CU(cudaMemcpyAsync(taps_last, c->lstaps.p, (size_t)M * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
     }
+    return finish(c, flags);
+}
+
+int prc_iq_mix_c64(const void* in, int in_kind, int64_t n, int mode, double fc, double fs, double phase_offset,
+                   prc_c64* out, int mem_kind, int device, void* stream, unsigned flags) {
+    if (!in || !out) return fail(PRC_E_INVALID, "in/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (in_kind < IQ_C64 || in_kind > IQ_I16) return fail(PRC_E_INVALID, "in_kind=%d invalid", in_kind);
+    if (mode < MIX_NONE || mode > MIX_FS64) return fail(PRC_E_INVALID, "mode=%d invalid", mode);
+    if (mode != MIX_NONE && !(fs != 0.0)) return fail(PRC_E_INVALID, "fs must not be 0");
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const void* din = in;
+    float2* dout = reinterpret_cast<float2*>(out);
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->fe_in.ensure(iq_bytes(in_kind, n)));
+        TRY(c->fe_out.ensure((size_t)n * sizeof(float2)));
+        CU(cudaMemcpyAsync(c->fe_in.p, in, iq_bytes(in_kind, n), cudaMemcpyHostToDevice, c->stream));
+        din = c->fe_in.p;
+        dout = c->fe_out.as<float2>();
+    }
+    TRY(mix_device(c, make_mix(din, in_kind, n, mode, fc, fs, phase_offset), dout));
+    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    return finish(c, flags);
+}
+
+int prc_resample_out_len(int64_t n_in, int up, int down, int nh, int64_t* n_out) {
+    if (!n_out) return fail(PRC_E_INVALID, "n_out must not be NULL");
+    ResampleGeo g;
+    TRY(resample_geo(n_in, up, down, nh, &g));
+    *n_out = g.n_out;
+    return PRC_OK;
+}
+
+int prc_frontend_c64(const void* in, int in_kind, int64_t n, int mode, double fc, double fs, double phase_offset,
+                     int up, int down, const double* h, int nh, prc_c64* out, int64_t out_capacity,
+                     int mem_kind, int device, void* stream, unsigned flags) {
+    if (!in || !out || !h) return fail(PRC_E_INVALID, "in/out/h must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (in_kind < IQ_C64 || in_kind > IQ_I16) return fail(PRC_E_INVALID, "in_kind=%d invalid", in_kind);
+    if (mode < MIX_NONE || mode > MIX_FS64) return fail(PRC_E_INVALID, "mode=%d invalid", mode);
+    if (mode != MIX_NONE && !(fs != 0.0)) return fail(PRC_E_INVALID, "fs must not be 0");
+    ResampleGeo g;
+    TRY(resample_geo(n, up, down, nh, &g));
+    if (out_capacity < g.n_out) return fail(PRC_E_INVALID, "out holds %lld samples, %lld needed", (long long)out_capacity, g.n_out);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const void* din = in;
+    float2* dout = reinterpret_cast<float2*>(out);
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->fe_in.ensure(iq_bytes(in_kind, n)));
+        TRY(c->fe_out.ensure((size_t)g.n_out * sizeof(float2)));
+        CU(cudaMemcpyAsync(c->fe_in.p, in, iq_bytes(in_kind, n), cudaMemcpyHostToDevice, c->stream));
+        din = c->fe_in.p;
+        dout = c->fe_out.as<float2>();
+    }
+    long long n_out = 0;
+    TRY(resample_device(c, make_mix(din, in_kind, n, mode, fc, fs, phase_offset), up, down, h, nh, dout, &n_out));
+    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n_out * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    return finish(c, flags);
+}
+
+int prc_cfar2d_f32(const void* x, int rows, int cols, int fw, int gw, const float* thresh, float* cr_out,
+                   uint8_t* det_out, int mem_kind, int device, void* stream, unsigned flags) {
+    if (!x || (!cr_out && !det_out)) return fail(PRC_E_INVALID, "x and one of cr_out/det_out must not be NULL");
+    if (det_out && !thresh) return fail(PRC_E_INVALID, "det_out needs a threshold");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (rows < 1 || cols < 1) return fail(PRC_E_INVALID, "rows=%d cols=%d invalid", rows, cols);
+    const bool cplx = (flags & PRC_FLAG_ABS_C64) != 0;
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t cells = (size_t)rows * cols;
+    const void* dx = x;
+    float* dcr = cr_out;
+    uint8_t* ddet = det_out;
+    if (mem_kind == PRC_MEM_HOST) {
+        const size_t inb = cells * (cplx ? sizeof(float2) : sizeof(float));
+        TRY(c->cf_in.ensure(inb));
+        CU(cudaMemcpyAsync(c->cf_in.p, x, inb, cudaMemcpyHostToDevice, c->stream));
+        dx = c->cf_in.p;
+        if (cr_out) { TRY(c->cf_cr.ensure(cells * sizeof(float))); dcr = c->cf_cr.as<float>(); }
+        if (det_out) { TRY(c->cf_det.ensure(cells)); ddet = c->cf_det.as<uint8_t>(); }
+    }
+    TRY(cfar_device(c, dx, cplx, rows, cols, fw, gw, thresh, dcr, ddet));
+    if (mem_kind == PRC_MEM_HOST) {
+        if (cr_out) CU(cudaMemcpyAsync(cr_out, dcr, cells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (det_out) CU(cudaMemcpyAsync(det_out, ddet, cells, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return finish(c, flags);
+}
+
+int prc_direct_xambg_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int range_bins, int freq_bins,
+                         double sample_rate, prc_c64* out, int mem_kind, int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (range_bins < 0 || freq_bins < 1) return fail(PRC_E_INVALID, "range_bins=%d freq_bins=%d invalid", range_bins, freq_bins);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const size_t ob = (size_t)freq_bins * (range_bins + 1) * sizeof(float2);
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    float2* dout = reinterpret_cast<float2*>(out);
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->ref.ensure(nb));
+        TRY(c->srv.ensure(nb));
+        TRY(c->out.ensure(ob));
+        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dout = c->out.as<float2>();
+    }
+    TRY(direct_xambg_device(c, dref, dsrv, n, range_bins, freq_bins, sample_rate, dout));
+    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, c->stream));
     return finish(c, flags);
 }
 

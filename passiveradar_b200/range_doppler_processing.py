@@ -75,3 +75,25 @@ def fast_xambg(refChannel, srvChannel, rangeBins, freqBins, inputLen=None, windo
                            out.ctypes.data, _lib.MEM_HOST, dev, None, 0)
     _lib.check(st)
     return out
+
+
+def direct_xambg(refChannel, srvChannel, rangeBins, freqBins, sampleRate, *, device=None):
+    ''' Direct Cross-Ambiguity Fuction (time domain method), computed on the GPU.
+
+    Args / returns as the reference (``range_doppler_processing.py:93-124``): per Doppler bin the
+    reference channel is frequency-shifted (float32 phase ramp, as ``frequency_shift`` does) and linearly
+    cross-correlated with the surveillance channel; ``ndarray`` of shape ``(freqBins, rangeBins + 1, 1)``.
+    '''
+    refChannel = np.asarray(refChannel)
+    srvChannel = np.asarray(srvChannel)
+    if refChannel.shape != srvChannel.shape:
+        raise ValueError('Input vectors must have the same length')
+    ref = _lib.as_c64(refChannel, "refChannel")
+    srv = _lib.as_c64(srvChannel, "srvChannel")
+    rangeBins, freqBins = int(rangeBins), int(freqBins)
+    out = np.empty((freqBins, rangeBins + 1, 1), dtype=np.complex64)
+    lib = _lib.load()
+    dev = _lib.current_device() if device is None else int(device)
+    _lib.check(lib.prc_direct_xambg_c64(ref.ctypes.data, srv.ctypes.data, ref.shape[0], rangeBins, freqBins,
+                                        float(sampleRate), out.ctypes.data, _lib.MEM_HOST, dev, None, 0))
+    return out

@@ -66,3 +66,16 @@ def frame_digest(ref: np.ndarray, srv: np.ndarray) -> np.ndarray:
         ref[picks], srv[picks],
         np.array([ref.astype(np.complex128).sum(), srv.astype(np.complex128).sum()]).astype(np.complex64),
     ])
+
+
+def raw_iq(n, kind="int8", seed=11):
+    """Seeded interleaved I/Q block of ``n`` complex samples as a receiver would deliver it
+    (``int8``: HackRF-style, ``int16``, or ``float32``); input of the front-end chain."""
+    rng = np.random.default_rng(seed)
+    if kind == "int8":
+        return rng.integers(-128, 128, size=2 * n, dtype=np.int8)
+    if kind == "int16":
+        return rng.integers(-2048, 2048, size=2 * n, dtype=np.int16)
+    if kind == "float32":
+        return rng.standard_normal(2 * n).astype(np.float32)
+    raise ValueError(f"unknown raw IQ kind {kind!r}")

@@ -60,4 +60,20 @@ LS_C1 = ["ls_c1_p1", "ls_c1_p0"]
 NLMS_ALL = ["nlms_small", "nlms_small_init", "nlms_peek0", "nlms_mid"]
 
 TOEP_ALL = ["toep_small", "toep_small_peek0", "toep_mid"]
-MULTI_ALL = ["multi_small", "multi_main"]
+MULTI_ALL = ["multi_small", "multi_fs_odd", "multi_main"]
+
+
+CFAR_ALL = ["cfar_main", "cfar_thresh", "cfar_odd", "cfar_tiny_map"]
+DIRECT_ALL = ["direct_small", "direct_odd", "direct_mid"]
+FRONT_SMALL = ["front_int8", "front_int16_py", "front_f32_short"]
+FRONT_BIG = ["front_chunk"]
+RESAMPLE_ALL = ["resample_c64", "resample_c128"]
+
+
+def front_inputs(g):
+    """(iq, fc, fs, phase_offset as the golden passed it, up, dn) of a front-end golden."""
+    iq = synth.raw_iq(int(g["n"]), str(g["kind"]), int(g["seed"]))
+    assert int(iq.astype(np.int64).sum()) == int(g["iq_crc"]) or str(g["kind"]) == "float32"
+    po = float(g["phase_offset"])
+    po = np.array([po]) if bool(g["po_array"]) else (int(po) if po == int(po) else po)
+    return iq, float(g["fc"]), float(g["fs"]), po, int(g["up"]), int(g["dn"])

@@ -39,7 +39,8 @@ sys.path.insert(0, os.environ.get("PR_REFERENCE", "/root/reference"))
 
 from passiveRadar.range_doppler_processing import fast_xambg          # noqa: E402  (the reference)
 from passiveRadar.clutter_removal import LS_Filter, NLMS_filter, LS_Filter_Toeplitz, LS_Filter_Multiple   # noqa: E402  (the reference)
-from passiveRadar.signal_utils import frequency_shift                 # noqa: E402  (the reference)
+from passiveRadar.signal_utils import frequency_shift, deinterleave_IQ, resample   # noqa: E402  (the reference)
+from passiveRadar.range_doppler_processing import direct_xambg        # noqa: E402  (the reference)
 from passiveradar_b200 import synth                                    # noqa: E402
 
 
@@ -186,6 +187,80 @@ def frame_case(name, n, F, R, profile, store_inputs, frame=0):
     save(name, **arrays)
 
 
+def load_reference_cfar():
+    """passiveRadar/target_detection.py uses np.float / np.int (removed in NumPy 1.24) in module-level dtype
+    tables that CFAR_2D never touches; alias it for the import only -- CFAR_2D itself runs unmodified."""
+    import builtins
+    added = []
+    for alias in ("float", "int", "bool", "complex", "object"):
+        if alias not in np.__dict__:
+            setattr(np, alias, getattr(builtins, alias))
+            added.append(alias)
+    try:
+        from passiveRadar.target_detection import CFAR_2D
+    finally:
+        for alias in added:
+            delattr(np, alias)
+    return CFAR_2D
+
+
+def cfar_map(rows, cols, seed):
+    rng = np.random.default_rng(seed)
+    x = np.abs(rng.standard_normal((rows, cols)) + 1j * rng.standard_normal((rows, cols))).astype(np.float32)
+    for (r, c, a) in [(rows // 2, cols // 3, 40.0), (3, cols - 2, 25.0), (rows - 1, 0, 30.0)]:
+        x[r % rows, c % cols] += np.float32(a)
+    return x
+
+
+def cfar_case(name, rows, cols, fw, gw, thresh=None, seed=5):
+    CFAR_2D = load_reference_cfar()
+    x = cfar_map(rows, cols, seed)
+    out = CFAR_2D(x, fw, gw, thresh)
+    print(f"{name}: {rows}x{cols} fw={fw} gw={gw} thresh={thresh} -> {out.dtype}")
+    save(name, x=x, fw=fw, gw=gw, thresh=np.float64(-1.0 if thresh is None else thresh), has_thresh=thresh is not None,
+         out=out)
+
+
+def direct_case(name, n, R, F, fs, profile, frame=0):
+    ref, srv = synth.make_frame(n, profile, frame)
+    t0 = time.time()
+    out = direct_xambg(ref, srv, R, F, fs)
+    print(f"{name}: n={n} R={R} F={F} fs={fs} {profile} {time.time() - t0:.2f}s")
+    save(name, n=n, R=R, F=F, fs=np.float64(fs), profile=profile, frame=frame, digest=synth.frame_digest(ref, srv), out=out)
+
+
+raw_iq = synth.raw_iq
+
+
+def front_case(name, n, kind, fc, fs, phase_offset, up, dn, seed=11, store_full=True, po_array=True):
+    iq = raw_iq(n, kind, seed)
+    po = np.array([phase_offset]) if po_array else phase_offset       # main.py:127-130 passes a (1,) float64 block
+    t0 = time.time()
+    x = deinterleave_IQ(iq)
+    xs = frequency_shift(x, fc, fs, po)
+    y = resample(xs, up, dn)
+    dt = time.time() - t0
+    idx = subsample_idx(n)
+    oidx = subsample_idx(y.shape[0])
+    arrays = dict(n=n, kind=kind, fc=np.float64(fc), fs=np.float64(fs), phase_offset=np.float64(phase_offset),
+                  po_array=po_array, up=up, dn=dn, seed=seed, iq_crc=np.int64(int(iq.astype(np.int64).sum())),
+                  x_idx=idx, deint_sub=x[idx], shift_sub=xs[idx], out_idx=oidx, out_sub=y[oidx],
+                  out_len=y.shape[0], out_sum=np.complex128(y.sum()), out_absmax=np.float64(np.abs(y).max()),
+                  shift_dtype=str(xs.dtype), out_dtype=str(y.dtype))
+    if store_full:
+        arrays.update(out=y)
+    print(f"{name}: n={n} {kind} fc={fc} fs={fs} po={phase_offset} {up}/{dn} -> {y.shape[0]} {y.dtype} {dt:.2f}s")
+    save(name, **arrays)
+
+
+def resample_case(name, n, dtype, up, dn, profile="P1"):
+    ref, _ = synth.make_frame(n, profile, 3)
+    x = ref.astype(dtype)
+    y = resample(x, up, dn)
+    print(f"{name}: n={n} {dtype} {up}/{dn} -> {y.shape[0]} {y.dtype}")
+    save(name, n=n, dtype=str(np.dtype(dtype)), up=up, dn=dn, profile=profile, out=y)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true", help="also BASELINE config 2 (minutes, ~9 GB RAM)")
@@ -258,6 +333,8 @@ def main():
         toeplitz_case("toep_mid", n=262144, filter_len=175, peek=10, profile="P1", store_inputs=False)
     if want("multi_small"):
         multiple_case("multi_small", n=8192, filter_len=24, sample_rate=8192.0, bins=[0, 1, -1], profile="P1")
+    if want("multi_fs_odd"):       # large phases at a non-power-of-two rate: pins numpy's reciprocal-multiply ramp
+        multiple_case("multi_fs_odd", n=8192, filter_len=24, sample_rate=250000.0, bins=[0, 20000.5, -3000.25], profile="P1")
     if want("multi_main"):
         # the shipped PRconfig.yaml: half-CPI chunks of 262144 samples, 175 range cells, IF rate 2.4e6*13/119
         multiple_case("multi_main", n=262144, filter_len=175, sample_rate=2.4e6 * 13 / 119, bins=[0, 1, -1, 2, -2],
@@ -288,6 +365,34 @@ def main():
                     store_inputs=False)
         if want("frame_c2_p0"):
             frame_case("frame_c2_p0", 2 ** 20, 256, 300, "P0", store_inputs=False)
+
+    # ---- rows either side of the hot path: front end, CFAR, direct_xambg
+    if want("cfar_main"):
+        cfar_case("cfar_main", 256, 301, 18, 4)
+    if want("cfar_thresh"):
+        cfar_case("cfar_thresh", 64, 101, 18, 4, thresh=3.0)
+    if want("cfar_odd"):
+        cfar_case("cfar_odd", 40, 33, 9, 3)
+    if want("cfar_tiny_map"):
+        cfar_case("cfar_tiny_map", 12, 20, 18, 4)
+    if want("direct_small"):
+        direct_case("direct_small", 4096, 20, 16, 4096.0, "P1")
+    if want("direct_odd"):
+        direct_case("direct_odd", 5000, 33, 8, 250000.0, "P0")
+    if want("direct_mid"):
+        direct_case("direct_mid", 65536, 40, 32, 262144.0, "P1")
+    if want("front_int8"):
+        front_case("front_int8", 120_000, "int8", 300_000.0, 2_400_000.0, 1.2345, 13, 119)
+    if want("front_int16_py"):
+        front_case("front_int16_py", 50_001, "int16", -12345.678, 1_000_000.0, 0, 3, 2, po_array=False)
+    if want("front_f32_short"):
+        front_case("front_f32_short", 700, "float32", 10.0, 1000.0, 0.5, 13, 119)
+    if want("front_chunk"):
+        front_case("front_chunk", 9_600_000, "int8", 300_000.0, 2_400_000.0, 2.0 * np.pi * 7 * 0.125, 13, 119, store_full=False)
+    if want("resample_c64"):
+        resample_case("resample_c64", 30_000, np.complex64, 13, 119)
+    if want("resample_c128"):
+        resample_case("resample_c128", 9_000, np.complex128, 1, 4)
 
 
 if __name__ == "__main__":

@@ -92,8 +92,12 @@ def test_install_swaps_hot_path_functions_of_a_reference_package(tmp_path, monke
         "def LS_Filter_Toeplitz(*a, **k):\n    return 'cpu'\n"
         "def LS_Filter_Multiple(*a, **k):\n    return 'cpu'\n"
         "def GAL_JPE(*a, **k):\n    return 'untouched'\n")
+    (pkg / "signal_utils.py").write_text("def resample(*a, **k):\n    return 'cpu'\ndef xcorr(*a, **k):\n    return 'untouched'\n")
+    (pkg / "target_detection.py").write_text("raise AttributeError('np.float')\n")     # as under NumPy 2
     monkeypatch.syspath_prepend(str(tmp_path))
     replaced = prb.install("fakeRadar")
+    from fakeRadar.signal_utils import resample, xcorr
+    assert resample is prb.resample and xcorr() == "untouched"
     assert "fakeRadar.range_doppler_processing.fast_xambg" in replaced
     from fakeRadar.clutter_removal import LS_Filter_Multiple, NLMS_filter, GAL_JPE, block_NLMS
     from fakeRadar.range_doppler_processing import fast_xambg
