@@ -120,6 +120,7 @@ struct Ctx {
     DBuf firb[3];             // Wm^T planes of the tensor-core FIR
     DBuf fe_in, fe_mid, fe_out, fe_hp, fe_ends;    // front end: raw IQ, mixed, resampled, polyphase taps, end points
     DBuf cf_in, cf_cr, cf_det, cf_part;            // CFAR_2D
+    uint64_t fe_hp_key = 0;                        // which taps fe_hp holds
     DBuf rs, clean2;          // LS_Filter_Toeplitz: rolled / frequency-shifted reference, ping-pong output
     DBuf cafplane[6];         // bf16 planes of the tensor-core CAF: x[3], s[3]
     DBuf tcplane[9];          // bf16 planes of the tensor-core path: x[3], s0[3], s1[3]
@@ -150,6 +151,8 @@ std::atomic<bool> g_attrs_set[64];
 std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
 int g_tune_nchunk = -1, g_tune_g = -1;
 int g_tile = 0;          // measured on B200: 10x10 beats 6x18 / 14x14 (109 vs 117 / 115 us, profiles/r01_tuning.md)
+int g_tma_l2 = 2;          // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B (PRC_TMA_L2)
+int g_tma = 1;             // TMA (cp.async.bulk.tensor) producers for the tcgen05 kernels (PRC_TMA=0: 16-byte cp.async loaders)
 int g_tc_fir = 1;          // tensor-core path for the clutter FIR (PRC_TC_FIR=0: FP32 fir_apply_kernel)
 int g_tc_caf = 1;          // tensor-core path for the CAF block sums as well (PRC_TC_CAF=0: FP32 lagstream)
 int g_tc = 1;              // tcgen05 Toeplitz-GEMM for the LS correlations (PRC_TC=0: FP32 lagstream kernel)
@@ -171,6 +174,8 @@ void read_env() {
     if (const char* e = getenv("PRC_TC")) g_tc = atoi(e);
     if (const char* e = getenv("PRC_TC_CAF")) g_tc_caf = atoi(e);
     if (const char* e = getenv("PRC_TC_FIR")) g_tc_fir = atoi(e);
+    if (const char* e = getenv("PRC_TMA")) g_tma = atoi(e);
+    if (const char* e = getenv("PRC_TMA_L2")) g_tma_l2 = atoi(e);
     if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
 }
 
@@ -180,8 +185,10 @@ int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagcorr_kernel<LC_TI, LC_TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(tc::firtc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(tc::toepcorr_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<6, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(lagstream_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -360,6 +367,58 @@ void launch_lagstream(dim3 grid, int threads, size_t smem, cudaStream_t st, cons
     }
 }
 
+// ---- tensor maps (TMA).  cuTensorMapEncodeTiled is a host-only driver call, resolved through the runtime
+// (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+std::once_flag g_encode_once;
+
+void resolve_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    });
+}
+// TMA producers need the driver's tensor-map encoder; without it the cp.async loaders (same layout family,
+// same speed) are used
+bool use_tma() {
+    if (!g_tma) return false;
+    resolve_encode();
+    return g_encode_tiled != nullptr;
+}
+
+// BF16, 2-D: element (c0, c1) = base[c1 * stride_elems + c0]; rows may overlap (stride_elems < inner)
+int make_map_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t stride_elems,
+                  uint32_t box_inner, uint32_t box_rows) {
+    resolve_encode();
+    if (!g_encode_tiled) return fail(PRC_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {stride_elems * 2};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t es[2] = {1, 1};
+    const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      (CUtensorMapL2promotion)g_tma_l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PRC_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return PRC_OK;
+}
+
+// maps of the Toeplitz-GEMM operands: x rows are 128 elements, s rows 256 * npass elements wide, both 128 apart
+int make_toep_maps(const tc::ToepParams& tp, tc::ToepMaps* m) {
+    const uint64_t rows = (uint64_t)tp.nk * tc::KSTEP;
+    for (int k = 0; k < tc::NPLANE; ++k) {
+        TRY(make_map_bf16(&m->x[k], tp.x[k], tc::ROW, rows, tc::ROW, 64, tc::KSTEP));
+        for (int pr = 0; pr < 2; ++pr)
+            TRY(make_map_bf16(&m->s[pr][k], tp.s[pr][k], (uint64_t)tp.npass * tc::NPASS, rows, tc::ROW, 64, tc::KSTEP));
+    }
+    return PRC_OK;
+}
+
 // Tensor-core CAF eligibility and geometry (shared by the frame pipeline, which lets the LS stage's prep
 // and FIR kernels write the CAF operands while the data is in registers, and by xambg_device)
 struct CafTc {
@@ -465,9 +524,13 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
         tp.kb = (int)(D / 1024); tp.nblk = F; tp.HT = ct.ht;
         tp.partial = c->partial.as<float2>();
         tp.debug_tile = nullptr; tp.debug_clk = nullptr;
+        tc::ToepMaps maps{};
+        const bool tma = use_tma();
+        if (tma) TRY(make_toep_maps(tp, &maps));
         {
             ProfScope ps(c, K_LAGCORR_CAF);
-            tc::toepcorr_kernel<false><<<c->nsm, tc::THREADS, tc::toep_smem_bytes(ct.ht), c->stream>>>(tp);
+            if (tma) tc::toepcorr_kernel<false, true><<<c->nsm, tc::THREADS, tc::toep_smem_bytes(ct.ht), c->stream>>>(tp, maps);
+            else tc::toepcorr_kernel<false, false><<<c->nsm, tc::THREADS, tc::toep_smem_bytes(ct.ht), c->stream>>>(tp, maps);
         }
         TRY(check_launch("toepcorr_kernel(caf)"));
         g.nchunk = ct.npass;
@@ -667,9 +730,13 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         tp.nk = tc_nk; tp.nlag = M; tp.npass = tc_npass; tp.ranges = tc_ranges; tp.HT = tc_ht;
         tp.partial = c->partial.as<float2>();
         tp.debug_tile = nullptr; tp.debug_clk = nullptr;
+        tc::ToepMaps maps{};
+        const bool tma = use_tma();
+        if (tma) TRY(make_toep_maps(tp, &maps));
         {
             ProfScope ps(c, K_LAGCORR_LS);
-            tc::toepcorr_kernel<true><<<2 * tc_npass * tc_ranges, tc::THREADS, tc::toep_smem_bytes(tc_ht), c->stream>>>(tp);
+            if (tma) tc::toepcorr_kernel<true, true><<<2 * tc_npass * tc_ranges, tc::THREADS, tc::toep_smem_bytes(tc_ht), c->stream>>>(tp, maps);
+            else tc::toepcorr_kernel<true, false><<<2 * tc_npass * tc_ranges, tc::THREADS, tc::toep_smem_bytes(tc_ht), c->stream>>>(tp, maps);
         }
         TRY(check_launch("toepcorr_kernel"));
         g.nchunk = tc_npass * tc_ranges;
@@ -873,7 +940,7 @@ int resample_geo(long long n_in, int up, int down, int nh, ResampleGeo* g) {
     g->n_pre_pad = down - half_len % down;
     g->n_pre_remove = (half_len + g->n_pre_pad) / down;
     g->n_out = (n_in * up + down - 1) / down;
-    g->tpp = ceil_div(g->n_pre_pad + nh, up);
+    g->tpp = ceil_div(g->n_pre_pad + nh, up) | 1;     // odd row stride: the `up` phase rows of the table start in distinct shared-memory banks
     return PRC_OK;
 }
 
@@ -897,13 +964,25 @@ int resample_device(Ctx* c, const MixParams& mix, int up_in, int down_in, const 
     const size_t smem = hp_bytes + (size_t)rp.span * sizeof(float2);
     if (smem > SMEM_LIMIT)
         return fail(PRC_E_INVALID, "resample %d/%d with %d taps needs %zu bytes of shared memory per CTA", g.up, g.down, nh, smem);
-    // polyphase table on the host (nh ~ 2.4k taps), staged through the stream
-    std::vector<float> hp((size_t)g.up * g.tpp, 0.f);
-    for (int k = g.n_pre_pad; k < g.n_pre_pad + nh; ++k) hp[(size_t)(k % g.up) * g.tpp + k / g.up] = (float)h[k - g.n_pre_pad];
-    TRY(c->fe_hp.ensure(hp.size() * sizeof(float)));
+    // polyphase table built on the host (nh ~ 2.4k taps) and cached per context: re-uploaded only when
+    // the taps change (FNV-1a over the doubles), so steady-state calls enqueue kernels only
+    uint64_t key = 1469598103934665603ull;
+    auto mixin = [&key](const void* ptr, size_t bytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(ptr);
+        for (size_t q = 0; q < bytes; ++q) { key ^= b[q]; key *= 1099511628211ull; }
+    };
+    mixin(h, (size_t)nh * sizeof(double));
+    mixin(&g.up, sizeof(int));
+    mixin(&g.down, sizeof(int));
     TRY(c->fe_ends.ensure(2 * sizeof(float2)));
-    CU(cudaMemcpyAsync(c->fe_hp.p, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));     // hp is a stack-lifetime host buffer
+    if (key != c->fe_hp_key || !c->fe_hp.p) {
+        std::vector<float> hp((size_t)g.up * g.tpp, 0.f);
+        for (int k = g.n_pre_pad; k < g.n_pre_pad + nh; ++k) hp[(size_t)(k % g.up) * g.tpp + k / g.up] = (float)h[k - g.n_pre_pad];
+        TRY(c->fe_hp.ensure(hp.size() * sizeof(float)));
+        CU(cudaMemcpyAsync(c->fe_hp.p, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));     // hp is a stack-lifetime host buffer
+        c->fe_hp_key = key;
+    }
     rp.hp = c->fe_hp.as<float>();
     rp.ends = c->fe_ends.as<float2>();
     static std::atomic<bool> attr_set[64];

@@ -26,6 +26,7 @@
 // cp.async copies straight from the interleaved BF16 planes -- no expanded matrix ever exists in HBM.  One CTA = one (problem, pass, K-range); warps 0-3 epilogue (TMEM -> diagonal sums),
 // warp 4 issues the MMAs, warps 5-8 load.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,6 +70,26 @@ struct ToepParams {
     long long* debug_clk;   // optional: phase timestamps of CTA 0
 };
 
+// ---- TMA producer (TMA = true) ------------------------------------------------------------------------------
+// Tensor maps of the BF16 planes: element (c0, c1) = plane[128 * c1 + c0], i.e. K-row c1 of the Toeplitz
+// operand starting at column c0.  Rows are 256 bytes apart but 256 * npass elements wide: they OVERLAP in
+// memory (cuTensorMapEncodeTiled accepts that, scripts/tc/tma_probe.cu), which is what materialises the
+// im2col operand without ever storing it.  Box = 64 elements x 16 K-rows, SWIZZLE_128B: it lands as 16 rows
+// of 128 bytes with the 16-byte chunk index XOR-ed with (row & 7) -- the UMMA operand layout, with the two
+// 8-row K groups of one 64-element MN group contiguous (SBO = 1 KB) and MN groups 2 KB apart (LBO).
+// Measured (profiles/r01_tuning.md): same speed as the cp.async loaders (the kernel is bound by shared-memory
+// bandwidth: 6 MMAs x 12 KB of operand reads + 36 KB of fill per 768-cycle K-step), but one elected thread
+// per stage instead of four full warps of address arithmetic; L2 promotion must be <= 128 B (256 B: 46 us).
+struct ToepMaps {
+    CUtensorMap x[NPLANE];
+    CUtensorMap s[2][NPLANE];
+};
+constexpr int TMA_BOX_BYTES = 64 * 2 * KSTEP;     // 2 KB: one 64-element MN group, both 8-row K groups
+constexpr int TMA_LBO = TMA_BOX_BYTES;            // stride between MN groups
+constexpr int TMA_SBO = ATOM_BYTES;               // stride between the two K groups inside a box
+constexpr int MAX_SLOTS = STAGES;
+constexpr int OPERAND_BYTES = STAGES * STAGE_BYTES;         // operand area of the dynamic shared memory
+
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -91,6 +112,19 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src));
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA: one thread arms the stage's mbarrier with the byte count, then issues 2-D tiled bulk-tensor copies
+// that complete on it.  With SWIZZLE_128B the box lands as rows of 128 bytes whose 16-byte chunk index is
+// XOR-ed with (row & 7) -- exactly the UMMA SWIZZLE_128B operand layout (scripts/tc/tma_probe.cu).
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -158,8 +192,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 struct __align__(16) ToepShared {
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
+    uint64_t full[MAX_SLOTS];
+    uint64_t empty[MAX_SLOTS];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
@@ -208,8 +242,8 @@ __device__ __forceinline__ ToepItem toep_item(const ToepParams& p, int it) {
 // buffered so the diagonal-sum epilogue of item i overlaps the MMAs of item i + 1 (CAF Doppler blocks).
 // Warps 0-3 and 9-12: epilogue; warp 4: MMA issue; warps 5-8: loaders.
 // dynamic shared memory: [stages x {A_b0, A_b1, A_b2, B_b0, B_b1, B_b2}] [8 x skew] [8 x 2 x HT floats]
-template <bool DUAL>
-__global__ void __launch_bounds__(THREADS, 1) toepcorr_kernel(const __grid_constant__ ToepParams p) {
+template <bool DUAL, bool TMA>
+__global__ void __launch_bounds__(THREADS, 1) toepcorr_kernel(const __grid_constant__ ToepParams p, const __grid_constant__ ToepMaps maps) {
     extern __shared__ __align__(1024) uint8_t tsm[];
     __shared__ ToepShared sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -217,11 +251,11 @@ __global__ void __launch_bounds__(THREADS, 1) toepcorr_kernel(const __grid_const
     const bool is_mma = warp == NUM_EPI_WARPS;
 
     uint8_t* stage_base = tsm;
-    float* skew = reinterpret_cast<float*>(tsm + STAGES * STAGE_BYTES);           // [8][SKEW_FLOATS]
+    float* skew = reinterpret_cast<float*>(tsm + OPERAND_BYTES);                     // [8][SKEW_FLOATS]
     float* cacc = skew + EPI_PARTS * SKEW_FLOATS;                                    // [8][2][HT]
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+        for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], EPI_PARTS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -233,7 +267,38 @@ __global__ void __launch_bounds__(THREADS, 1) toepcorr_kernel(const __grid_const
     const uint32_t tmem = sh.tmem_base;
     if (p.debug_clk && blockIdx.x == 0 && threadIdx.x == 0) p.debug_clk[0] = clock64();
 
-    if (is_loader) {
+    if (TMA && is_loader) {
+        // ======================= TMA producers: lane 0 of loader warp w owns pipeline stage w.  Per K-step: arm
+        // the stage's mbarrier with 36 KB, then 18 bulk-tensor copies (per plane: 2 boxes of the x rows, 4 boxes
+        // of the overlapping s rows).
+        const int lw = warp - NUM_EPI_WARPS - 1;
+        if (lane == 0) {
+#pragma unroll
+            for (int pl = 0; pl < NPLANE; ++pl) { tma_prefetch_desc(&maps.x[pl]); tma_prefetch_desc(&maps.s[0][pl]); tma_prefetch_desc(&maps.s[1][pl]); }
+            int g = 0;
+            for (int it = 0;; ++it) {
+                const ToepItem item = toep_item(p, it);
+                if (!item.valid) break;
+                for (int t = 0; t < item.kcount; ++t, ++g) {
+                    if ((g & (STAGES - 1)) != lw) continue;
+                    if (g >= STAGES) mbar_wait(&sh.empty[lw], ((g / STAGES) - 1) & 1);
+                    uint8_t* st = stage_base + lw * STAGE_BYTES;
+                    const int row0 = (item.kbeg + t) * KSTEP;
+                    mbar_expect_tx(&sh.full[lw], STAGE_BYTES);
+#pragma unroll
+                    for (int pl = 0; pl < NPLANE; ++pl) {
+#pragma unroll
+                        for (int m = 0; m < ROW / 64; ++m)
+                            tma_load_2d(st + pl * A_BYTES + m * TMA_BOX_BYTES, &maps.x[pl], 64 * m, row0, &sh.full[lw]);
+#pragma unroll
+                        for (int m = 0; m < NPASS / 64; ++m)
+                            tma_load_2d(st + NPLANE * A_BYTES + pl * B_BYTES + m * TMA_BOX_BYTES, &maps.s[item.prob][pl],
+                                        item.pass * NPASS + 64 * m, row0, &sh.full[lw]);
+                    }
+                }
+            }
+        }
+    } else if (is_loader) {
         // ======================= loaders: 16-byte cp.async into 128B-swizzled MN-major tiles.
         // Loader warp w owns pipeline stage w: it issues the whole 36 KB stage, waits for ITS copies only,
         // publishes them to the async proxy and arrives.  (A fence after cp.async.wait_group N > 0 also
@@ -298,8 +363,8 @@ __global__ void __launch_bounds__(THREADS, 1) toepcorr_kernel(const __grid_const
                     uint64_t da[NPLANE], db[NPLANE];
 #pragma unroll
                     for (int pl = 0; pl < NPLANE; ++pl) {
-                        da[pl] = make_desc_sw128(a0 + pl * A_BYTES, MN_LBO, A_SBO);
-                        db[pl] = make_desc_sw128(b0 + pl * B_BYTES, MN_LBO, B_SBO);
+                        da[pl] = make_desc_sw128(a0 + pl * A_BYTES, TMA ? TMA_LBO : MN_LBO, TMA ? TMA_SBO : A_SBO);
+                        db[pl] = make_desc_sw128(b0 + pl * B_BYTES, TMA ? TMA_LBO : MN_LBO, TMA ? TMA_SBO : B_SBO);
                     }
                     // The tensor core truncates once per MMA when it adds into the fp32 accumulator (measured
                     // bias ~ -steps * 2^-25 relative).  DUAL keeps the dominant b0*b0' chain alone in
@@ -574,7 +639,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Pr
 }
 
 inline size_t toep_smem_bytes(int HT) {
-    return (size_t)STAGES * STAGE_BYTES + EPI_PARTS * SKEW_FLOATS * sizeof(float) + (size_t)EPI_PARTS * 2 * HT * sizeof(float);
+    return (size_t)OPERAND_BYTES + EPI_PARTS * SKEW_FLOATS * sizeof(float) + (size_t)EPI_PARTS * 2 * HT * sizeof(float);
 }
 
 }  // namespace tc

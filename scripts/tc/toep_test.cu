@@ -58,12 +58,12 @@ int main(int argc, char** argv) {
         q.kb = atoi(argv[4]); q.nblk = nk / q.kb; q.ranges = 0; q.debug_tile = nullptr;
         for (int k = 0; k < 3; ++k) q.s[0][k] = s1p[k];
         float2* dp2; CK(cudaMalloc(&dp2, (size_t)q.nblk * npass * HT * sizeof(float2))); q.partial = dp2;
-        CK(cudaFuncSetAttribute(toepcorr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)toep_smem_bytes(HT)));
+        CK(cudaFuncSetAttribute(toepcorr_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)toep_smem_bytes(HT)));
         cudaEvent_t a0, a1; cudaEventCreate(&a0); cudaEventCreate(&a1);
         for (int rep = 0; rep < 3; ++rep) {
             CK(cudaMemset(dclk, 0, 512));
             cudaEventRecord(a0);
-            toepcorr_kernel<false><<<148, THREADS, toep_smem_bytes(HT)>>>(q);
+            toepcorr_kernel<false, false><<<148, THREADS, toep_smem_bytes(HT)>>>(q, ToepMaps{});
             cudaEventRecord(a1);
             CK(cudaDeviceSynchronize());
         }
@@ -74,12 +74,12 @@ int main(int argc, char** argv) {
         CK(cudaMemset(dclk, 0, 512));
     }
     const size_t smem = toep_smem_bytes(HT);
-    CK(cudaFuncSetAttribute(toepcorr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(toepcorr_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 4; ++rep) {
         if (rep == 1) { p.debug_tile = nullptr; }      // rep 0 dumps the tile, the timed reps do not
         cudaEventRecord(e0);
-        toepcorr_kernel<true><<<2 * npass * ranges, THREADS, smem>>>(p);
+        toepcorr_kernel<true, false><<<2 * npass * ranges, THREADS, smem>>>(p, ToepMaps{});
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
     }
