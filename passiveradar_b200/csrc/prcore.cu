@@ -705,7 +705,9 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
             pp.zero_outside[0] = pp.zero_outside[1] = linear ? 1 : 0;
             for (int k = 0; k < 3; ++k) { pp.plane[0][k] = c->tcplane[3 + k].as<uint16_t>(); pp.plane[1][k] = c->tcplane[6 + k].as<uint16_t>(); }
             pp.win = fold ? win32 : nullptr;
-            pp.refw = fold ? c->refw.as<float2>() : nullptr;
+            // the complex64 ref*window is only needed by the FP32 CAF; the tensor-core CAF takes its x planes (cafx)
+            const bool need_refw = fold && !(caf && caf->on);
+            pp.refw = need_refw ? c->refw.as<float2>() : nullptr;
             pp.n = (int)n;
             pp.len = slen + lead;
             if (fold && caf && caf->on) {          // also emit the CAF x operand (ref * window, shifted by D/2)
@@ -720,7 +722,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
             tc::tc_prep_kernel<<<dim3(ceil_div(slen + lead, 1024), 2), 256, 0, c->stream>>>(pp);
         }
         TRY(check_launch("tc_prep_kernel"));
-        if (fold) *refw_ready = true;
+        if (fold && !(caf && caf->on)) *refw_ready = true;
         tc::ToepParams tp{};
         for (int k = 0; k < 3; ++k) {
             tp.x[k] = alias_x ? c->tcplane[3 + k].as<uint16_t>() + 2 * lead : c->tcplane[k].as<uint16_t>();

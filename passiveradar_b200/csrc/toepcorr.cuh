@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const __grid_constant__ Pr
         const bool ok = (q0 + k < p.len) && (!p.zero_outside[sg] || (lin >= 0 && lin < p.n)) &&
                         (p.n_valid[sg] == 0 || q0 + k < p.n_valid[sg]);
         v[k] = ok ? sig[i] : make_float2(0.f, 0.f);
-        w[k] = (sg == 0 && p.refw && lin >= 0 && lin < p.n) ? p.win[lin] : 1.f;
+        w[k] = (sg == 0 && p.win && lin >= 0 && lin < p.n) ? p.win[lin] : 1.f;
     }
     uint32_t o[3][4];
 #pragma unroll
