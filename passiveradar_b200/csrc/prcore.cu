@@ -122,6 +122,9 @@ struct Ctx {
     DBuf fe_in, fe_mid, fe_out, fe_hp, fe_ends;    // front end: raw IQ, mixed, resampled, polyphase taps, end points
     DBuf cf_in, cf_cr, cf_det, cf_part;            // CFAR_2D
     uint64_t fe_hp_key = 0;                        // which taps fe_hp holds
+    // tensor maps of the last LS / CAF launch of this context: the planes live in DBufs, so the operand addresses
+    // repeat from frame to frame and the nine cuTensorMapEncodeTiled calls per launch are paid once
+    struct MapCache { bool valid = false; const void* ptr[9] = {nullptr}; int nk = 0, npass = 0; tc::ToepMaps maps; } map_cache[2];
     DBuf rs, clean2;          // LS_Filter_Toeplitz: rolled / frequency-shifted reference, ping-pong output
     DBuf cafplane[6];         // bf16 planes of the tensor-core CAF: x[3], s[3]
     DBuf tcplane[9];          // bf16 planes of the tensor-core path: x[3], s0[3], s1[3]
@@ -425,6 +428,24 @@ int make_toep_maps(const tc::ToepParams& tp, tc::ToepMaps* m) {
     return PRC_OK;
 }
 
+// cached variant: slot 0 = LS, slot 1 = CAF
+int cached_toep_maps(Ctx* c, int slot, const tc::ToepParams& tp, const tc::ToepMaps** out) {
+    Ctx::MapCache& mc = c->map_cache[slot];
+    const void* ptr[9];
+    for (int k = 0; k < 3; ++k) { ptr[k] = tp.x[k]; ptr[3 + k] = tp.s[0][k]; ptr[6 + k] = tp.s[1][k]; }
+    bool same = mc.valid && mc.nk == tp.nk && mc.npass == tp.npass;
+    for (int k = 0; same && k < 9; ++k) same = mc.ptr[k] == ptr[k];
+    if (!same) {
+        mc.valid = false;
+        TRY(make_toep_maps(tp, &mc.maps));
+        for (int k = 0; k < 9; ++k) mc.ptr[k] = ptr[k];
+        mc.nk = tp.nk; mc.npass = tp.npass;
+        mc.valid = true;
+    }
+    *out = &mc.maps;
+    return PRC_OK;
+}
+
 // Tensor-core CAF eligibility and geometry (shared by the frame pipeline, which lets the LS stage's prep
 // and FIR kernels write the CAF operands while the data is in registers, and by xambg_device)
 struct CafTc {
@@ -530,9 +551,11 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
         tp.kb = (int)(D / 1024); tp.nblk = F; tp.HT = ct.ht;
         tp.partial = c->partial.as<float2>();
         tp.debug_tile = nullptr; tp.debug_clk = nullptr;
-        tc::ToepMaps maps{};
+        static const tc::ToepMaps no_maps{};
+        const tc::ToepMaps* mp = &no_maps;
         const bool tma = use_tma();
-        if (tma) TRY(make_toep_maps(tp, &maps));
+        if (tma) TRY(cached_toep_maps(c, 1, tp, &mp));
+        const tc::ToepMaps& maps = *mp;
         {
             ProfScope ps(c, K_LAGCORR_CAF);
             if (tma) tc::toepcorr_kernel<false, true><<<c->nsm, tc::THREADS, tc::toep_smem_bytes(ct.ht), c->stream>>>(tp, maps);
@@ -738,9 +761,11 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         tp.nk = tc_nk; tp.nlag = M; tp.npass = tc_npass; tp.ranges = tc_ranges; tp.HT = tc_ht;
         tp.partial = c->partial.as<float2>();
         tp.debug_tile = nullptr; tp.debug_clk = nullptr;
-        tc::ToepMaps maps{};
+        static const tc::ToepMaps no_maps{};
+        const tc::ToepMaps* mp = &no_maps;
         const bool tma = use_tma();
-        if (tma) TRY(make_toep_maps(tp, &maps));
+        if (tma) TRY(cached_toep_maps(c, 0, tp, &mp));
+        const tc::ToepMaps& maps = *mp;
         {
             ProfScope ps(c, K_LAGCORR_LS);
             if (tma) tc::toepcorr_kernel<true, true><<<2 * tc_npass * tc_ranges, tc::THREADS, tc::toep_smem_bytes(tc_ht), c->stream>>>(tp, maps);
