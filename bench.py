@@ -348,6 +348,26 @@ def run_b200(args, cfg, rank, world, local_rank):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = frames_total / e2e_s
 
+    # ---- what the host link can carry: plain pinned-memory H2D copies of the same 256 MiB, nothing else running
+    # (context for e2e, which moves 16.8 MB per frame over PCIe)
+    h2d_peak = None
+    try:
+        if rank == 0:
+            src = torch.from_numpy(ref_h.reshape(-1).view(np.float32))
+            dst = torch.empty_like(src, device=dev)
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize(dev)
+            h2d_peak = 4 * src.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+            del dst
+    except Exception:       # context only: never let it break the bench line
+        h2d_peak = None
+
     # ---- per-kernel durations: CUDA events on the launching stream, one frame at a time on one stream
     roofline = None
     per_kernel = {}
@@ -429,7 +449,11 @@ def run_b200(args, cfg, rank, world, local_rank):
                        "cache": f"inputs {B * 2 * n * 8 / 2 ** 20:.0f} MiB per step > 126 MB L2 (no flush needed)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 2 * n * 8,
                     "d2h_bytes_per_step": B * F * (R + 1) * 8,
-                    "api": "passiveradar_b200.frames.FramePipeline.run_host (pinned host ndarrays)"},
+                    "api": "passiveradar_b200.frames.FramePipeline.run_host (pinned host ndarrays)",
+                    "h2d_GBps": round(B * 2 * n * 8 * args.steps * world / e2e_s / 1e9 / world, 2),
+                    "h2d_link_GBps": round(h2d_peak, 2) if h2d_peak else None,
+                    "note": "h2d_GBps = input bytes per second per GPU through the timed region; h2d_link_GBps = plain "
+                            "pinned-memory cudaMemcpy of the same buffers measured beside it (the PCIe ceiling of e2e)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
