@@ -219,3 +219,38 @@ def ls_filter_multiple_oracle(refChannel, srvChannel, filterLen, sampleRate, dop
         ref_k = refChannel if doppler == 0 else frequency_shift_oracle(refChannel, doppler, sampleRate)
         cleaned = ls_filter_toeplitz_oracle(ref_k, cleaned, filterLen)
     return cleaned
+
+
+def nlms_block_exact(refChannel, srvChannel, filterLen, mu, peek=10, L=32, dtype=np.complex64):
+    """The NLMS recurrence of the reference evaluated L samples at a time WITHOUT changing its values
+    (the statement ``nlms_block_kernel`` implements; not ``block_NLMS``, whose taps are frozen in a block).
+
+    With the taps W at the start of a block and g(m,k) = u_m^H u_k, p_m = g(m,m):
+        r_k = d_k - W^H u_k
+        e_k = r_k - mu * sum_{m<k} e_m g(m,k) / p_m          (forward substitution)
+        W  <- W + mu * sum_m u_m conj(e_m) / p_m
+    which is the sequential recurrence (clutter_removal.py:211-215) with w_k eliminated."""
+    ref = np.asarray(refChannel).astype(dtype)
+    srv = np.asarray(srvChannel).astype(dtype)
+    M = filterLen + peek
+    n = srv.shape[0]
+    nsteps = n - M
+    real = np.float32 if dtype == np.complex64 else np.float64
+    W = np.zeros(M, dtype)
+    out = np.zeros(n, dtype)
+    k0 = 0
+    while k0 < nsteps:
+        Lb = min(L, nsteps - k0)
+        U = np.stack([ref[k + 1: k + M + 1][::-1] for k in range(k0, k0 + Lb)], axis=1)      # M x Lb, column k = u_k
+        r = srv[filterLen + k0: filterLen + k0 + Lb] - W.conj() @ U
+        G = U.conj().T @ U
+        p = G.diagonal().real.astype(real)
+        e = np.zeros(Lb, dtype)
+        for m in range(Lb):
+            e[m] = r[m]
+            if m + 1 < Lb:
+                r[m + 1:] = r[m + 1:] - dtype(mu) * e[m] * G[m, m + 1:] / p[m]
+        W = (W + (U * (dtype(mu) * e.conj() / p)[None, :]).sum(axis=1)).astype(dtype)
+        out[filterLen + k0: filterLen + k0 + Lb] = e
+        k0 += Lb
+    return out, W

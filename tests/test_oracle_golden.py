@@ -145,3 +145,16 @@ def test_multiple_oracle_matches_reference(name):
     assert G.rel_inf(out[g["out_idx"]], g["out_sub"], den=float(g["srv_absmax"])) < 1e-9
     sh = co.frequency_shift_oracle(ref, float(g["bins"][-1]), float(g["sample_rate"]))
     assert np.array_equal(sh[g["out_idx"]], g["shift_sample"])
+
+
+@pytest.mark.parametrize("name", ["nlms_small", "nlms_peek0"])
+@pytest.mark.parametrize("L", [8, 32])
+def test_block_exact_nlms_is_the_reference_recurrence(name, L):
+    """The triangular-system form nlms_block_kernel evaluates equals the reference's sample-serial NLMS
+    (golden produced by the reference) up to complex64 round-off."""
+    g = G.load(name)
+    ref, srv = G.inputs(g)
+    out, taps = co.nlms_block_exact(ref, srv, int(g["filter_len"]), float(g["mu"]), int(g["peek"]), L)
+    den = np.abs(srv).max()
+    assert np.abs(out - g["out"]).max() / den <= 2e-6
+    assert np.abs(taps - g["taps"]).max() / np.abs(g["taps"]).max() <= 5e-6
