@@ -81,7 +81,7 @@ struct ResampleParams {
     int up, down;
     int nh;               // taps in h (2 * half_len + 1)
     int n_pre_pad, n_pre_remove;
-    int tpp;              // taps per phase, ceil((n_pre_pad + nh) / up) rounded up to a multiple of 4 (zero padded)
+    int tpp;              // taps per phase = ceil((n_pre_pad + nh) / up), made odd (table row stride)
     long long n_out;
     const float* hp;      // polyphase table [up][tpp]: hp[ph][j] = hpad[ph + j * up]
     float2 x0, x1;        // mixed end points x[0], x[n-1] (line extension); filled by resample_ends_kernel
@@ -128,18 +128,19 @@ __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_const
     const int ph = (int)(T - ih * p.up);                     // hpad index of the newest sample: k = ph + j * up
     const float* h = hp + (size_t)ph * p.tpp;
     const float2* x = xs + (ih - i_lo);                      // x[-j] = xext[ih - j]
-    // four taps per iteration: one 128-bit load of the phase's taps (rows are 16-byte aligned, zero padded to a
-    // multiple of four) and four 64-bit loads of consecutive samples; four independent accumulator chains
-    float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f, cr = 0.f, ci = 0.f, dr = 0.f, di = 0.f;
-    for (int j = 0; j < p.tpp; j += 4) {
-        const float4 hh = *reinterpret_cast<const float4*>(h + j);
-        const float2 v0 = x[-j], v1 = x[-j - 1], v2 = x[-j - 2], v3 = x[-j - 3];
-        ar = fmaf(hh.x, v0.x, ar); ai = fmaf(hh.x, v0.y, ai);
-        br = fmaf(hh.y, v1.x, br); bi = fmaf(hh.y, v1.y, bi);
-        cr = fmaf(hh.z, v2.x, cr); ci = fmaf(hh.z, v2.y, ci);
-        dr = fmaf(hh.w, v3.x, dr); di = fmaf(hh.w, v3.y, di);
+    float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;            // two chains: shorter dependency, pairwise-like sum
+    int j = 0;
+    for (; j + 1 < p.tpp; j += 2) {
+        const float h0 = h[j], h1 = h[j + 1];
+        const float2 v0 = x[-j], v1 = x[-j - 1];
+        ar = fmaf(h0, v0.x, ar); ai = fmaf(h0, v0.y, ai);
+        br = fmaf(h1, v1.x, br); bi = fmaf(h1, v1.y, bi);
     }
-    ar += cr; ai += ci; br += dr; bi += di;
+    if (j < p.tpp) {
+        const float h0 = h[j];
+        const float2 v0 = x[-j];
+        ar = fmaf(h0, v0.x, ar); ai = fmaf(h0, v0.y, ai);
+    }
     out[m] = make_float2(ar + br, ai + bi);
 }
 
