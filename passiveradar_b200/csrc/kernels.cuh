@@ -692,6 +692,7 @@ struct DopplerParams {
     // samples of a block, the last one, i = j*bstride + boff, is added here)
     const float2* bx;
     const float2* bs;
+    const float* bwin;       // optional: bx is the unweighted reference, multiply by bwin[i]
     long long bstride, boff;
     int n;
 };
@@ -699,7 +700,12 @@ struct DopplerParams {
 __device__ __forceinline__ float2 doppler_boundary(const DopplerParams& p, int j, int k) {
     const long long i = (long long)j * p.bstride + p.boff;
     if (p.bx == nullptr || i < 0 || i >= p.n) return make_float2(0.f, 0.f);
-    const float2 xv = p.bx[i];
+    float2 xv = p.bx[i];
+    if (p.bwin) {                                  // x = ref * window formed here (no complex64 copy of it exists)
+        const float w = p.bwin[i];
+        xv.x *= w;
+        xv.y *= w;
+    }
     const float2 sv = p.bs[(i + (p.R - k)) % p.n];
     return make_float2(xv.x * sv.x + xv.y * sv.y, xv.y * sv.x - xv.x * sv.y);      // x * conj(s)
 }

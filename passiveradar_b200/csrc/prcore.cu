@@ -499,12 +499,18 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     Geo g{};
     long long d_per_cta = 0;
     const float2* bnd_x = nullptr;                  // boundary-sample correction of the tensor-core path
+    const float* bnd_w_all = nullptr;               // ... window to apply to bnd_x on the fly (bnd_x unweighted)
     const CafTc ct = (ntaps == D + 1 && c0 == D / 2) ? caf_tc_plan(c, n, R, F, taps != nullptr) : CafTc{};
     if (ct.on) {
         // ---- tensor-core CAF: one (Doppler block, pass) item per accumulation, persistent CTAs
+        // ref * window as complex64 is needed to build the x planes here; when the LS stage already wrote them
+        // (caf_planes_ready) only the F boundary samples use it, and those are weighted on the fly
         const float2* xw = ref;
+        const float* bnd_w = nullptr;
         if (win32 && refw_ready) {
             xw = c->refw.as<float2>();
+        } else if (win32 && caf_planes_ready) {
+            bnd_w = win32;
         } else if (win32) {
             TRY(c->refw.ensure((size_t)n * sizeof(float2)));
             {
@@ -559,6 +565,7 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
         g.nchunk = ct.npass;
         g.HT = ct.ht;
         bnd_x = xw;
+        bnd_w_all = bnd_w;
     } else if (g_stream && taps == nullptr && ntaps >= 64) {   // tiny Doppler blocks: one flush per block would dominate
         StreamGeo sg;
         TRY(choose_stream((int)ntaps, F, 1, R + 1, c->nsm, &sg));
@@ -638,7 +645,7 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     d.out = out;
     d.F = F; d.R = R; d.nchunk = g.nchunk; d.HT = g.HT;
     d.blk_len = (int)ntaps; d.per_cta = d_per_cta;
-    d.bx = bnd_x; d.bs = srv; d.bstride = D; d.boff = c0; d.n = (int)n;
+    d.bx = bnd_x; d.bs = srv; d.bwin = bnd_x ? bnd_w_all : nullptr; d.bstride = D; d.boff = c0; d.n = (int)n;
     int logF = 0;
     while ((1 << logF) < F) ++logF;
     d.logF = logF;
