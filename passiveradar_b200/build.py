@@ -16,8 +16,9 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libprcore.so")
 SOURCES = [os.path.join(CSRC, "prcore.cu")]
-HEADERS = [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "nlms.cuh"),
-           os.path.join(ROOT, "include", "prcore.h")]
+# every header prcore.cu includes: a stale library after editing one of them is the worst kind of bug
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
+          [os.path.join(ROOT, "include", "prcore.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
