@@ -177,6 +177,33 @@ def block_nlms_oracle_c(ref, srv, filter_len, mu, peek=10, block_len=1, initial_
     return out, taps
 
 
+def block_nlms_truth_c(ref, srv, filter_len, mu, peek=10, block_len=1, initial_taps=None):
+    """The recurrence of ``block_nlms_oracle`` with every operation in float64 (oracle/nlms_oracle.c,
+    ``nlms_truth_c128``): how far the complex64 reference is from the exact recurrence.  Returns
+    (out, taps) as complex128."""
+    import ctypes as C
+    from . import build as _b
+    lib = C.CDLL(_b.build())
+    fn = lib.nlms_truth_c128
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_double, C.c_int,
+                   C.c_void_p, C.c_void_p, C.c_void_p]
+    ref = np.ascontiguousarray(ref, dtype=np.complex64)
+    srv = np.ascontiguousarray(srv, dtype=np.complex64)
+    init = None
+    if initial_taps is not None:
+        init = np.ascontiguousarray(initial_taps, dtype=np.complex64)
+        filter_len = init.shape[0] - peek
+    m = filter_len + peek
+    out = np.empty(srv.shape[0], dtype=np.complex128)
+    taps = np.empty(m, dtype=np.complex128)
+    st = fn(ref.ctypes.data, srv.ctypes.data, srv.shape[0], filter_len, peek, float(mu), block_len,
+            None if init is None else init.ctypes.data, out.ctypes.data, taps.ctypes.data)
+    if st != 0:
+        raise MemoryError("nlms_truth_c128 failed")
+    return out, taps
+
+
 # ------------------------------------------------------------ LS_Filter_Toeplitz / LS_Filter_Multiple
 # (SURVEY.md section 8f rank 1: the clutter filter main.py:169-176 actually calls)
 

@@ -66,3 +66,49 @@ int nlms_oracle_c64(const c64* ref, const c64* srv, long n, int filter_len, int 
     free(w); free(grad);
     return 0;
 }
+
+/* The same recurrence with every operation in double (inputs are the complex64 samples): the float64
+ * "truth" that tells how far the complex64 reference itself is from the exact recurrence. */
+typedef struct { double re, im; } c128;
+
+int nlms_truth_c128(const c64* ref, const c64* srv, long n, int filter_len, int peek, double mu,
+                    int block_len, const c64* init, c128* out, c128* taps_out)
+{
+    const int M = filter_len + peek;
+    const long nsteps = n - M;
+    c128* w = (c128*)calloc((size_t)(M > 0 ? M : 1), sizeof(c128));
+    c128* grad = (c128*)calloc((size_t)(M > 0 ? M : 1), sizeof(c128));
+    if (!w || !grad) { free(w); free(grad); return -1; }
+    if (init) for (int j = 0; j < M; ++j) { w[j].re = init[j].re; w[j].im = init[j].im; }
+    memset(out, 0, (size_t)n * sizeof(c128));
+    int in_block = 0;
+    for (long k = 0; k < nsteps; ++k) {
+        const c64* top = ref + M + k;
+        double dr = 0.0, di = 0.0, nrm = 0.0;
+        for (int j = 0; j < M; ++j) {
+            const double ur = top[-j].re, ui = top[-j].im;
+            dr += w[j].re * ur + w[j].im * ui;
+            di += w[j].re * ui - w[j].im * ur;
+            nrm += ur * ur + ui * ui;
+        }
+        const double er = (double)srv[k + filter_len].re - dr;
+        const double ei = (double)srv[k + filter_len].im - di;
+        out[k + filter_len].re = er;
+        out[k + filter_len].im = ei;
+        for (int j = 0; j < M; ++j) {
+            const double ur = top[-j].re, ui = top[-j].im;
+            grad[j].re += mu * (ur * er + ui * ei) / nrm;
+            grad[j].im += mu * (ui * er - ur * ei) / nrm;
+        }
+        if (++in_block == block_len || k == nsteps - 1) {
+            for (int j = 0; j < M; ++j) {
+                w[j].re += grad[j].re; w[j].im += grad[j].im;
+                grad[j].re = 0.0; grad[j].im = 0.0;
+            }
+            in_block = 0;
+        }
+    }
+    if (taps_out) memcpy(taps_out, w, (size_t)M * sizeof(c128));
+    free(w); free(grad);
+    return 0;
+}

@@ -28,6 +28,7 @@
 #include "frontend.cuh"
 #include "detect.cuh"
 #include "nlms.cuh"
+#include "nlms_block.cuh"
 
 namespace {
 
@@ -154,6 +155,7 @@ std::atomic<bool> g_attrs_set[64];
 std::atomic<uint64_t> g_epoch{1};                      // bumped by prc_shutdown
 int g_tune_nchunk = -1, g_tune_g = -1;
 int g_tile = 0;          // measured on B200: 10x10 beats 6x18 / 14x14 (109 vs 117 / 115 us, profiles/r01_tuning.md)
+int g_nlms_block = 1;       // block-exact NLMS kernel for NLMS_filter (PRC_NLMS_BLOCK=0: sample-serial kernel)
 int g_tma_l2 = 2;          // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B (PRC_TMA_L2)
 int g_tma = 1;             // TMA (cp.async.bulk.tensor) producers for the tcgen05 kernels (PRC_TMA=0: 16-byte cp.async loaders)
 int g_tc_fir = 1;          // tensor-core path for the clutter FIR (PRC_TC_FIR=0: FP32 fir_apply_kernel)
@@ -178,6 +180,7 @@ void read_env() {
     if (const char* e = getenv("PRC_TC_CAF")) g_tc_caf = atoi(e);
     if (const char* e = getenv("PRC_TC_FIR")) g_tc_fir = atoi(e);
     if (const char* e = getenv("PRC_TMA")) g_tma = atoi(e);
+    if (const char* e = getenv("PRC_NLMS_BLOCK")) g_nlms_block = atoi(e);
     if (const char* e = getenv("PRC_TMA_L2")) g_tma_l2 = atoi(e);
     if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
 }
@@ -208,6 +211,9 @@ int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(nlms_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(nlms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(nlms_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_block_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     g_attrs_set[device].store(true);
     return PRC_OK;
 }
@@ -1111,6 +1117,15 @@ int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int f
     const int threads = std::min(1024, ((ceil_div(M, kt) + 31) / 32) * 32);
     const size_t sm = (size_t)(NLMS_TILE + ((M + 1) & ~1) + NLMS_TILE) * sizeof(float2) + 64 * sizeof(float4);
     ProfScope ps(c, K_NLMS);
+    if (block_len == 1 && g_nlms_block) {
+        // NLMS_filter semantics: exact evaluation 32 samples at a time (nlms_block.cuh), 4x the speed of the
+        // sample-serial kernel at config 4
+        const size_t sb = nlms_block_smem(M);
+        if (kt == 1) nlms_block_kernel<1><<<1, NB_THREADS, sb, c->stream>>>(p);
+        else if (kt == 2) nlms_block_kernel<2><<<1, NB_THREADS, sb, c->stream>>>(p);
+        else nlms_block_kernel<4><<<1, NB_THREADS, sb, c->stream>>>(p);
+        return check_launch("nlms_block_kernel");
+    }
     if (kt == 1) nlms_kernel<1><<<1, threads, sm, c->stream>>>(p);
     else if (kt == 2) nlms_kernel<2><<<1, threads, sm, c->stream>>>(p);
     else nlms_kernel<4><<<1, threads, sm, c->stream>>>(p);

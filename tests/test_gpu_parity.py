@@ -255,14 +255,21 @@ def test_nlms_short_input_is_all_zero():
 # ------------------------------------------------------------------ BASELINE config 4 (2M samples, NLMS)
 def test_nlms_config4_matches_c_oracle():
     """2**21-sample CPI, filterLen = 400 (+10 peek): the Python reference needs ~18 s for this, the
-    plain-C oracle (pinned to the reference by tests/test_oracle_golden.py) a few seconds."""
+    plain-C oracle (pinned to the reference by tests/test_oracle_golden.py) a few seconds.  Over 2M samples
+    the complex64 recurrence of the reference is itself 6e-6 from the float64 recurrence, so -- as for
+    LS_Filter -- the GPU must be within 1e-5 of the TRUTH and within 1e-5 + 1.2 x (reference-vs-truth) of the
+    reference."""
     from oracle import clutter_oracle as co
     n, fl = 2 ** 21, 400
     ref, srv = synth.make_frame(n, "P1", frame=4)
     want, ww = co.block_nlms_oracle_c(ref, srv, fl, 0.05, 10, 1)
+    truth, tw = co.block_nlms_truth_c(ref, srv, fl, 0.05, 10, 1)
     got, gw = prb.NLMS_filter(ref, srv, fl, 0.05, 10, None, True)
-    assert G.rel_inf(got, want) <= TOL
-    assert G.rel_inf(gw, ww) <= 5e-5
+    den = float(np.abs(truth).max())
+    e_ref = G.rel_inf(want, truth, den=den)
+    assert G.rel_inf(got, truth, den=den) <= TOL, "NLMS_filter vs float64 truth"
+    assert G.rel_inf(got, want, den=den) <= TOL + 1.2 * e_ref, "NLMS_filter vs reference arithmetic"
+    assert G.rel_inf(gw, tw) <= 5e-5
     assert not got[:fl].any() and not got[-10:].any()
     wantb, wwb = co.block_nlms_oracle_c(ref, srv, fl, 0.05, 10, 64)
     gotb, gwb = prb.block_NLMS(ref, srv, fl, 0.05, 10, 64, None, True)
