@@ -426,7 +426,8 @@ def run_b200(args, cfg, rank, world, local_rank):
         else:
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": round(ach / peaks["hbm_gbs"], 5),
-                        "fp32_frac_of_peak": round(per_kernel[dom]["alg_TFLOPs"] / fp32_peak, 4), **common}
+                        "fp32_frac_of_peak": (round(per_kernel[dom]["alg_TFLOPs"] / fp32_peak, 4)
+                                              if per_kernel[dom]["alg_TFLOPs"] is not None else None), **common}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
