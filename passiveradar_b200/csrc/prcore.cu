@@ -851,9 +851,12 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     if (use_fir_tc) {
         for (int k = 0; k < 3; ++k) TRY(c->firb[k].ensure((size_t)tc::FIR_N * fir_kv * sizeof(uint16_t)));
         {
-            ProfScope ps(c, K_FIR);
+            ProfScope ps(c, K_MISC);          // the taps-matrix builder is bookkeeping, not the FIR itself
             tc::fir_bmat_kernel<<<ceil_div(tc::FIR_N * fir_kv, 256), 256, 0, c->stream>>>(
                 c->lstaps.as<float2>(), M, fir_shift, fir_kv, c->firb[0].as<uint16_t>(), c->firb[1].as<uint16_t>(), c->firb[2].as<uint16_t>());
+        }
+        {
+            ProfScope ps(c, K_FIR);
             tc::FirTcParams ft{};
             for (int k = 0; k < 3; ++k) { ft.z[k] = c->tcplane[3 + k].as<uint16_t>(); ft.b[k] = c->firb[k].as<uint16_t>(); }
             ft.zoff = fir_zoff;
