@@ -1,4 +1,5 @@
-// nlms_block.cuh -- NLMS_filter (reference clutter_removal.py:189-249) evaluated 32 samples at a time, exactly.
+// nlms_block.cuh -- NLMS_filter (reference clutter_removal.py:189-249) evaluated 32 samples at a time, exactly
+// (and block_NLMS, whose taps are frozen inside a user block, with the same machinery minus the substitution).
 //
 // The reference recurrence
 //     e_k = d_k - w_k^H u_k,   w_{k+1} = w_k + mu u_k conj(e_k) / (u_k^H u_k),   u_k[j] = ref[M + k - j]
@@ -56,6 +57,13 @@ __global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_con
         w[r] = (p.init && j < M) ? p.init[j] : make_float2(0.f, 0.f);
         if (j < Mpad) Ws[j] = (j < M) ? w[r] : make_float2(0.f, 0.f);
     }
+    // block_NLMS (block_len > 1): taps frozen inside a user block -- no substitution, the
+    // increments are collected in `grad` and applied when the user block ends; sub-blocks never straddle one
+    const bool frozen = p.block_len > 1;
+    float2 grad[KT];
+#pragma unroll
+    for (int r = 0; r < KT; ++r) grad[r] = make_float2(0.f, 0.f);
+    int in_block = 0;
     const int S = (M + 31) / 32;                      // taps per warp in the dot-product phase
     const long long nref = p.n;
 
@@ -68,8 +76,10 @@ __global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_con
         }
         for (int q = tid; q < tl; q += NB_THREADS) dtile[q] = p.srv[p.filter_len + ts + q];
         __syncthreads();
-        for (int kk0 = 0; kk0 < tl; kk0 += NB_L) {
-            const int Lb = min(NB_L, tl - kk0);
+        int Lb = 0;
+        for (int kk0 = 0; kk0 < tl; kk0 += Lb) {
+            Lb = min(NB_L, tl - kk0);
+            if (frozen) Lb = min(Lb, p.block_len - in_block);
             // ---- phase A1: partial dot products  sum_{j in warp's segment} conj(W[j]) * u_{kk0+lane}[j]
             {
                 float ar = 0.f, ai = 0.f;
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_con
                 }
                 const float2 d = lane < Lb ? dtile[kk0 + lane] : make_float2(0.f, 0.f);
                 float rr = d.x - sr, ri = d.y - si;
-                for (int m = 0; m < Lb - 1; ++m) {
+                for (int m = 0; m < (frozen ? 0 : Lb - 1); ++m) {
                     // coefficient of e_m in sample `lane`: mu g(m, lane) / p_m  (independent of the chain: loads first)
                     const float ip = invp[m];
                     const float2 g = Gs[m * (NB_L + 1) + ((lane - m) & 31)];
@@ -167,8 +177,28 @@ __global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_con
                         tr = fmaf(u1.x, c1.x, tr); tr = fmaf(-u1.y, c1.y, tr);
                         ti = fmaf(u1.x, c1.y, ti); ti = fmaf(u1.y, c1.x, ti);
                     }
-                    w[r] = make_float2(w[r].x + (sr + tr), w[r].y + (si + ti));
-                    Ws[j] = w[r];
+                    if (!frozen) {
+                        w[r] = make_float2(w[r].x + (sr + tr), w[r].y + (si + ti));
+                        Ws[j] = w[r];
+                    } else {
+                        grad[r].x += sr + tr;
+                        grad[r].y += si + ti;
+                    }
+                }
+            }
+            if (frozen) {
+                in_block += Lb;
+                if (in_block == p.block_len || ts + kk0 + Lb == nsteps) {     // user block complete: apply its gradient
+#pragma unroll
+                    for (int r = 0; r < KT; ++r) {
+                        const int j = tid + r * NB_THREADS;
+                        if (j < M) {
+                            w[r].x += grad[r].x; w[r].y += grad[r].y;
+                            Ws[j] = w[r];
+                        }
+                        grad[r] = make_float2(0.f, 0.f);
+                    }
+                    in_block = 0;
                 }
             }
             __syncthreads();

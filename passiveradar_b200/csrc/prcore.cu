@@ -1120,9 +1120,9 @@ int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int f
     const int threads = std::min(1024, ((ceil_div(M, kt) + 31) / 32) * 32);
     const size_t sm = (size_t)(NLMS_TILE + ((M + 1) & ~1) + NLMS_TILE) * sizeof(float2) + 64 * sizeof(float4);
     ProfScope ps(c, K_NLMS);
-    if (block_len == 1 && g_nlms_block) {
-        // NLMS_filter semantics: exact evaluation 32 samples at a time (nlms_block.cuh), 4x the speed of the
-        // sample-serial kernel at config 4
+    if (g_nlms_block) {
+        // exact evaluation 32 samples at a time (nlms_block.cuh), 4x the speed of the sample-serial kernel at
+        // config 4; block_len > 1 (block_NLMS) freezes the taps inside a user block
         const size_t sb = nlms_block_smem(M);
         if (kt == 1) nlms_block_kernel<1><<<1, NB_THREADS, sb, c->stream>>>(p);
         else if (kt == 2) nlms_block_kernel<2><<<1, NB_THREADS, sb, c->stream>>>(p);
