@@ -444,7 +444,7 @@ def run_b200(args, cfg, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; f64 Toeplitz solve)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; heavy sums as fp32-accurate BF16x3 tensor-core products with fp32 accumulation; f64 Toeplitz solve)", "data": "synthetic",
             "config": {"workload": cfg["name"], "frames_per_step_per_gpu": B, "slots": args.slots,
                        "profile": args.profile, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                        "cache": f"inputs {B * 2 * n * 8 / 2 ** 20:.0f} MiB per step > 126 MB L2 (no flush needed)"},
