@@ -63,8 +63,11 @@ def fir_decimate_shim():
         signal.decimate = real
 
 
+OUT_DIR = os.environ.get("PR_GOLDEN_OUT", HERE)       # tests regenerate into a scratch directory
+
+
 def save(name, **arrays):
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(OUT_DIR, name + ".npz")
     np.savez_compressed(path, **arrays)
     print(f"  wrote {name}.npz ({os.path.getsize(path) / 1024:.1f} KiB)")
 
