@@ -37,7 +37,7 @@ extern "C" {
 
 typedef struct prc_c64 { float re, im; } prc_c64;
 
-#define PRC_VERSION 100          /* 0.1.0 */
+#define PRC_VERSION 200          /* 0.2.0 */
 
 /* status codes */
 #define PRC_OK            0
@@ -150,6 +150,28 @@ int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n,
                   int range_bins, int freq_bins, const void* window,
                   prc_c64* out_map, prc_c64* taps_out, prc_c64* cleaned_out,
                   int mem_kind, int device, void* stream, unsigned flags);
+
+/* prc_frames_c64: the same composition for `nframes` frames in one call -- frame i reads ref + i*frame_stride and
+ * srv + i*frame_stride (strides in samples; device or host pointers as mem_kind says) and writes
+ * out_maps + i*freq_bins*(range_bins+1), taps_out + i*(filter_len+peek), cleaned_out + i*frame_stride.  This is the unit
+ * of work of the dask graph (one chunk = one frame, main.py:169-194) handed over several chunks at a time, so that one
+ * launch of each kernel covers the whole batch (gridDim.y = frame).  prc_frame_c64 is nframes = 1.
+ * With PRC_FLAG_ASYNC the Toeplitz-solve status of every frame stays on the device: prc_ls_status() reads it back
+ * (0 = ok, 1 = normal equations not positive definite) after synchronising `stream`.
+ */
+int prc_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                   int filter_len, int peek, float reg, int range_bins, int freq_bins, const void* window,
+                   prc_c64* out_maps, prc_c64* taps_out, prc_c64* cleaned_out,
+                   int mem_kind, int device, void* stream, unsigned flags);
+int prc_ls_status(int device, void* stream, int* status, int nframes);
+
+/* ---- run-time switches (also read once from the environment: PRC_FFT, PRC_FFT_MIN_N) ----------------
+ *   "fft"        1 (default): LS correlations, clutter FIR and CAF block sums as FFT-domain block correlations
+ *                (csrc/fftcorr.cuh);  0: direct form on tcgen05 / FP32 (csrc/toepcorr.cuh, firtc.cuh, lagstream.cuh)
+ *   "fft_min_n"  smallest channel length the FFT-domain path takes (default 8192)
+ */
+int prc_set_option(const char* name, int value);
+int prc_get_option(const char* name, int* value);
 
 /* ---- direct (time-domain) cross-ambiguity function ------------------------------------------------
  * Replaces direct_xambg(), reference passiveRadar/range_doppler_processing.py:93-124: for Doppler bin f

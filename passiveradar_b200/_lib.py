@@ -60,6 +60,11 @@ SIGNATURES = {
                                _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_frame_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                 C.c_void_p, _c64p, _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_frames_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                 C.c_void_p, _c64p, _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_ls_status": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int]),
+    "prc_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "prc_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "prc_direct_xambg_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int, C.c_double, _c64p,
                                        C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_iq_mix_c64": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
@@ -92,11 +97,18 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            if not build_if_missing:
-                raise OSError(f"{LIB_PATH} not found")
+        if build_if_missing:
+            # rebuild when the library is missing OR older than any source/header (a stale .so after an edit is
+            # the worst kind of bug); a no-op when up to date.  Without nvcc an existing library is used as is
+            # (the GPU box receives the library built here).
             from . import build as _build
-            _build.build()
+            try:
+                _build.build(force=False)
+            except RuntimeError:
+                if not os.path.exists(LIB_PATH):
+                    raise
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} not found")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
@@ -115,6 +127,17 @@ def check(status: int):
     if status == PRC_E_NOMEM:
         raise MemoryError(msg)
     raise PrcoreError(status, msg)
+
+
+def set_option(name: str, value: int):
+    """Run-time switch of the library (include/prcore.h: "fft", "fft_min_n")."""
+    check(load().prc_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_int(0)
+    check(load().prc_get_option(name.encode(), C.byref(v)))
+    return v.value
 
 
 def device_count() -> int:

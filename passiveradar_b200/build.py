@@ -36,25 +36,45 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found; libprcore.so cannot be built (there is no CPU fallback)")
 
 
+HASH = os.path.join(PKG, "libprcore.hash")
+
+
+def source_hash() -> str:
+    """sha256 over every source, header and the compiler flags: what the library was built from.  File times are
+    not used -- the snapshot that carries the built library to the GPU box does not keep them."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
-    if not os.path.exists(LIB):
+    if not (os.path.exists(LIB) and os.path.exists(HASH)):
         return False
-    t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
+    with open(HASH) as f:
+        return f.read().strip() == source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
+    tmp = LIB + f".tmp{os.getpid()}"           # concurrent builders (torchrun ranks) never see a half-written library
     cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC,
-                                          "-o", LIB] + SOURCES
+                                          "-o", tmp] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode == 0:
+        os.replace(tmp, LIB)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libprcore.so")
     with open(os.path.join(PKG, "libprcore.ptxas.log"), "w") as f:
         f.write(res.stdout + res.stderr)
+    with open(HASH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

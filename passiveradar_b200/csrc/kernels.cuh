@@ -504,6 +504,8 @@ __global__ void __launch_bounds__(E == 1 ? 1024 : 512) levinson_kernel(const __g
     double2* edge = part + 4;         //   [2][32][2]  last (newQ, newb) of every warp
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    // one CTA per frame of a batch: [frame][2][nchunk][HT] partials, [frame][M] taps, [frame] status
+    const float2* const gpartial = p.partial + (size_t)blockIdx.x * 2 * p.nchunk * p.HT;
 
     // ---- phase A: fp64 sum of the chunk partials in a fixed order, conjugate
     {
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(E == 1 ? 1024 : 512) levinson_kernel(const __g
             const int pt = tid / nval, v = tid - pt * nval;
             if (pt < nparts) {
                 const int prob = v / M, l = v - prob * M;
-                const float2* src = p.partial + (size_t)prob * p.nchunk * p.HT + l;
+                const float2* src = gpartial + (size_t)prob * p.nchunk * p.HT + l;
                 double sx = 0.0, sy = 0.0;
 #pragma unroll 8
                 for (int c = pt; c < p.nchunk; c += nparts) {
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(E == 1 ? 1024 : 512) levinson_kernel(const __g
                 for (int k = 0; k < nparts; ++k) { sx += part[k * nval + v2].x; sy += part[k * nval + v2].y; }
             } else {
                 const int prob = v2 / M, l = v2 - prob * M;
-                const float2* src = p.partial + (size_t)prob * p.nchunk * p.HT + l;
+                const float2* src = gpartial + (size_t)prob * p.nchunk * p.HT + l;
 #pragma unroll 8
                 for (int c = 0; c < p.nchunk; ++c) {
                     const float2 q = src[(size_t)c * p.HT];
@@ -660,9 +662,9 @@ __global__ void __launch_bounds__(E == 1 ? 1024 : 512) levinson_kernel(const __g
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int j = tid * E + e;
-        if (j < M) p.taps[j] = make_float2((float)x[e].x, (float)x[e].y);
+        if (j < M) p.taps[(size_t)blockIdx.x * M + j] = make_float2((float)x[e].x, (float)x[e].y);
     }
-    if (tid == 0) *p.status = bad;
+    if (tid == 0) p.status[blockIdx.x] = bad;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -695,6 +697,7 @@ struct DopplerParams {
     const float* bwin;       // optional: bx is the unweighted reference, multiply by bwin[i]
     long long bstride, boff;
     int n;
+    long long partial_fstride, out_fstride;   // batch of frames in blockIdx.y (float2 elements; 0 for a single frame)
 };
 
 __device__ __forceinline__ float2 doppler_boundary(const DopplerParams& p, int j, int k) {
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(256) doppler_fft_pow2_kernel(const __grid_cons
         const int k = k0 + c;
         float2 sum = make_float2(0.f, 0.f);
         if (k <= p.R) {
-            const float2* src = p.partial + (size_t)j * p.nchunk * p.HT + (p.R - k);
+            const float2* src = p.partial + (size_t)blockIdx.y * p.partial_fstride + (size_t)j * p.nchunk * p.HT + (p.R - k);
             const int rows = doppler_rows(p, j);
             for (int ch = 0; ch < rows; ++ch) {
                 const float2 v = src[(size_t)ch * p.HT];
@@ -764,7 +767,7 @@ __global__ void __launch_bounds__(256) doppler_fft_pow2_kernel(const __grid_cons
         const int k = k0 + c;
         if (k <= p.R) {
             const int f = (fp + half) & (F - 1);
-            p.out[(size_t)f * (p.R + 1) + k] = a[idx];
+            p.out[(size_t)blockIdx.y * p.out_fstride + (size_t)f * (p.R + 1) + k] = a[idx];
         }
     }
 }

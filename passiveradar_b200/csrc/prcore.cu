@@ -29,6 +29,7 @@
 #include "detect.cuh"
 #include "nlms.cuh"
 #include "nlms_block.cuh"
+#include "fftcorr.cuh"
 
 namespace {
 
@@ -131,6 +132,9 @@ struct Ctx {
     DBuf refw, ref, srv, out, clean, partial, win32, win64, dtaps32, dtaps64, lstaps, tw, pbuf, status,
         nl_init, nl_taps;
     int tw_F = 0;
+    int status_slot = 0;      // which int of `status` the direct-form Toeplitz solve reports to
+    DBuf fft_tw[3], wp_fir, wp_caf, fftP;     // FFT-domain path: twiddle tables (L = 1024 / 2048 / 4096), taps spectra, CAF block sums
+    bool fft_tw_ready[3] = {false, false, false};
     std::vector<ProfRec> recs;
     void release() {
         cudaSetDevice(device);
@@ -139,6 +143,9 @@ struct Ctx {
         for (DBuf& b : firb) b.release();
         rs.release();
         clean2.release();
+        for (DBuf& b : fft_tw) b.release();
+        for (bool& r : fft_tw_ready) r = false;
+        for (DBuf* b : {&wp_fir, &wp_caf, &fftP}) b->release();
         for (DBuf* b : {&fe_in, &fe_mid, &fe_out, &fe_hp, &fe_ends, &cf_in, &cf_cr, &cf_det, &cf_part}) b->release();
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
@@ -163,6 +170,8 @@ int g_tc_caf = 1;          // tensor-core path for the CAF block sums as well (P
 int g_tc = 1;              // tcgen05 Toeplitz-GEMM for the LS correlations (PRC_TC=0: FP32 lagstream kernel)
 int g_stream = 1;          // persistent pipelined lag-correlation kernel (PRC_STREAM=0: one-shot kernel)
 int g_packed = 1;          // FFMA2 kernels (PRC_PACKED=0 selects the scalar-FFMA variant for A/B runs)
+std::atomic<int> g_fft{1};            // FFT-domain correlation / overlap-save kernels (fftcorr.cuh); PRC_FFT=0: tcgen05 / FP32 direct form
+std::atomic<int> g_fft_min_n{8192};   // ... for channels of at least this many samples (PRC_FFT_MIN_N)
 std::once_flag g_env_once;
 
 struct TlsCtx {
@@ -183,6 +192,8 @@ void read_env() {
     if (const char* e = getenv("PRC_NLMS_BLOCK")) g_nlms_block = atoi(e);
     if (const char* e = getenv("PRC_TMA_L2")) g_tma_l2 = atoi(e);
     if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
+    if (const char* e = getenv("PRC_FFT")) g_fft.store(atoi(e));
+    if (const char* e = getenv("PRC_FFT_MIN_N")) g_fft_min_n.store(atoi(e));
 }
 
 int set_kernel_attrs(int device) {
@@ -214,6 +225,16 @@ int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(nlms_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(nlms_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(nlms_block_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+#define PRC_FFT_ATTRS(R3)                                                                                              \
+    CU(cudaFuncSetAttribute(fftc::lscorr_fft_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));           \
+    CU(cudaFuncSetAttribute(fftc::taps_spectrum_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));        \
+    CU(cudaFuncSetAttribute(fftc::fir_fft_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));              \
+    CU(cudaFuncSetAttribute(fftc::caf_fft_kernel<R3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));       \
+    CU(cudaFuncSetAttribute(fftc::caf_fft_kernel<R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    PRC_FFT_ATTRS(4)
+    PRC_FFT_ATTRS(8)
+    PRC_FFT_ATTRS(16)
+#undef PRC_FFT_ATTRS
     g_attrs_set[device].store(true);
     return PRC_OK;
 }
@@ -470,6 +491,187 @@ CafTc caf_tc_plan(const Ctx* c, long long n, int R, int F, bool has_taps) {
     return t;
 }
 
+// --------------------------------------------------------------------------- FFT-domain path (fftcorr.cuh)
+// A batch of frames: nf channels pairs `stride` samples apart (inputs), results laid out frame after frame.
+struct Batch {
+    int nf = 1;
+    long long stride = 0;
+};
+
+inline int r3_index(int r3) { return r3 == 4 ? 0 : (r3 == 8 ? 1 : 2); }
+inline size_t fft_smem(int r3) { return (size_t)(2 * 16 * 17 * r3 + 256 * r3 + 16 * r3) * sizeof(float2); }
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// R3 = 4 / 8 / 16  <->  L = 1024 / 2048 / 4096
+#define PRC_R3_SWITCH(r3, STMT)                        \
+    switch (r3) {                                      \
+        case 4: { constexpr int R3 = 4; STMT; } break; \
+        case 8: { constexpr int R3 = 8; STMT; } break; \
+        default: { constexpr int R3 = 16; STMT; } break; \
+    }
+
+int fft_twiddles(Ctx* c, int r3, const float2** tw) {
+    const int k = r3_index(r3);
+    const int cnt = 256 * r3 + 16 * r3;
+    if (!c->fft_tw_ready[k]) {
+        TRY(c->fft_tw[k].ensure((size_t)cnt * sizeof(float2)));
+        PRC_R3_SWITCH(r3, (fft::fft_twiddle_kernel<R3><<<ceil_div(cnt, 256), 256, 0, c->stream>>>(c->fft_tw[k].as<float2>())));
+        TRY(check_launch("fft_twiddle_kernel"));
+        c->fft_tw_ready[k] = true;
+    }
+    *tw = c->fft_tw[k].as<float2>();
+    return PRC_OK;
+}
+
+// ---- LS correlations: block partition of the channel
+struct LsFftPlan {
+    bool on = false;
+    int r3 = 8, nb = 0, Bu = 0, last = 0, bpc = 0, ncta = 0, HT = 0;
+};
+
+LsFftPlan ls_fft_plan(const Ctx* c, long long n, int M, int nf) {
+    LsFftPlan pl;
+    if (!g_fft.load() || n < g_fft_min_n.load() || M < 1 || M > 2048) return pl;
+    pl.r3 = M <= 1024 ? 8 : 16;
+    const int L = 256 * pl.r3, B = L / 2;
+    if (n < 2 * L) return pl;
+    const long long nb0 = (n + B - 1) / B;
+    bool found = false;
+    for (long long nb = std::max<long long>(nb0, 2); nb <= nb0 + 8 && !found; ++nb) {
+        const long long Bu = (n + nb - 1) / nb;
+        const long long last = n - (nb - 1) * Bu;
+        // every block must be followed by at least M - 1 samples of the next one, and lags < M must not alias
+        if (last >= std::max(M - 1, 1) && Bu >= M - 1 && Bu <= B && M <= L - Bu + 1) {
+            pl.nb = (int)nb; pl.Bu = (int)Bu; pl.last = (int)last;
+            found = true;
+        }
+    }
+    if (!found) return pl;
+    // CTAs of one transform group (16 R3 threads); ~3 resident per SM over the whole batch, >= 4 blocks each so
+    // that the look-ahead block and the two final transforms stay a small share
+    const long long want = std::max<long long>(1, (3ll * c->nsm + nf - 1) / nf);
+    pl.bpc = (int)std::max<long long>(4, (pl.nb + want - 1) / want);
+    pl.ncta = ceil_div(pl.nb, pl.bpc);
+    pl.HT = (M + 1) & ~1;
+    pl.on = true;
+    return pl;
+}
+
+int ls_fft_corr(Ctx* c, const LsFftPlan& pl, const float2* ref, const float2* srv, long long n, Batch bt, int M, int peek,
+                bool linear) {
+    const float2* tw;
+    TRY(fft_twiddles(c, pl.r3, &tw));
+    TRY(c->partial.ensure((size_t)bt.nf * 2 * pl.ncta * pl.HT * sizeof(float2)));
+    fftc::LsCorrParams p{};
+    p.ref = ref; p.srv = srv; p.frame_stride = bt.stride;
+    p.n = (int)n; p.M = M; p.peek = peek; p.linear = linear ? 1 : 0;
+    p.nb = pl.nb; p.Bu = pl.Bu; p.last = pl.last; p.bpc = pl.bpc;
+    p.partial = c->partial.as<float2>(); p.HT = pl.HT; p.tw = tw;
+    {
+        ProfScope ps(c, K_LAGCORR_LS);
+        PRC_R3_SWITCH(pl.r3, (fftc::lscorr_fft_kernel<R3><<<dim3(pl.ncta, bt.nf), 16 * R3, fft_smem(R3), c->stream>>>(p)));
+    }
+    return check_launch("lscorr_fft_kernel");
+}
+
+// (T + reg I) w = rhs for nf frames: taps -> c->lstaps [nf][M], status -> c->status [nf]
+int levinson_launch(Ctx* c, int nchunk, int HT, int M, double reg, int nf) {
+    TRY(c->lstaps.ensure((size_t)nf * M * sizeof(float2)));
+    TRY(c->status.ensure((size_t)nf * sizeof(int)));
+    LevinsonParams lp{};
+    lp.partial = c->partial.as<float2>();
+    lp.nchunk = nchunk; lp.HT = HT; lp.M = M; lp.reg = reg;
+    lp.taps = c->lstaps.as<float2>();
+    lp.status = c->status.as<int>();
+    {
+        ProfScope ps(c, K_LEVINSON);
+        if (M <= 1024) levinson_kernel<1><<<nf, 1024, levinson_smem(M, 1024), c->stream>>>(lp);
+        else levinson_kernel<4><<<nf, 512, levinson_smem(M, 512), c->stream>>>(lp);
+    }
+    return check_launch("levinson_kernel");
+}
+
+// W' of c->lstaps for transform length 256 r3 -> wp [nf][L]
+int taps_spectrum(Ctx* c, int r3, int M, int nf, DBuf* wp) {
+    const float2* tw;
+    TRY(fft_twiddles(c, r3, &tw));
+    TRY(wp->ensure((size_t)nf * 256 * r3 * sizeof(float2)));
+    fftc::TapSpecParams p{};
+    p.taps = c->lstaps.as<float2>(); p.M = M; p.wp = wp->as<float2>(); p.tw = tw;
+    {
+        ProfScope ps(c, K_MISC);
+        PRC_R3_SWITCH(r3, (fftc::taps_spectrum_kernel<R3><<<nf, 16 * R3, fft_smem(R3), c->stream>>>(p)));
+    }
+    return check_launch("taps_spectrum_kernel");
+}
+
+// out = srv - FIR(ref, c->lstaps) by overlap-save (circular, or zero-extended when linear)
+int fir_fft(Ctx* c, int r3, const float2* ref, const float2* srv, float2* out, long long n, Batch bt, int M, int peek,
+            bool linear) {
+    const float2* tw;
+    TRY(fft_twiddles(c, r3, &tw));
+    TRY(taps_spectrum(c, r3, M, bt.nf, &c->wp_fir));
+    const int L = 256 * r3;
+    fftc::FirFftParams p{};
+    p.ref = ref; p.srv = srv; p.out = out; p.frame_stride = bt.stride;
+    p.wp = c->wp_fir.as<float2>();
+    p.n = (int)n; p.M = M; p.peek = peek; p.linear = linear ? 1 : 0;
+    p.nseg = ceil_div(n, L - M + 1);
+    p.tw = tw;
+    const int per_frame = std::max(1, std::min(p.nseg, ceil_div(4 * c->nsm, bt.nf)));
+    {
+        ProfScope ps(c, K_FIR);
+        PRC_R3_SWITCH(r3, (fftc::fir_fft_kernel<R3><<<dim3(per_frame, bt.nf), 16 * R3, fft_smem(R3), c->stream>>>(p)));
+    }
+    return check_launch("fir_fft_kernel");
+}
+
+// ---- CAF block sums
+struct CafFftPlan {
+    bool on = false;
+    int r3 = 8, Bmax = 0, HT = 0;
+};
+
+// mfuse: taps of the clutter filter fused into the surveillance operand (0: none)
+CafFftPlan caf_fft_plan(long long n, int R, int F, long long ntaps, long long D, bool boxcar, int mfuse) {
+    CafFftPlan pl;
+    if (!g_fft.load() || n < g_fft_min_n.load() || !boxcar || D < 32 || F < 1) return pl;
+    double best = 0.0;
+    for (int r3 : {4, 8, 16}) {
+        const int L = 256 * r3;
+        const long long bmax = (long long)L - R - std::max(mfuse - 1, 0);
+        if (bmax < L / 4 || n < L) continue;
+        const long long nseg = (ntaps + bmax - 1) / bmax;
+        const double cost = (double)(nseg * (mfuse ? 3 : 2) + 1) * L * ilog2(L);
+        if (!pl.on || cost < best) {
+            pl.on = true; pl.r3 = r3; pl.Bmax = (int)bmax; best = cost;
+        }
+    }
+    pl.HT = (R + 2) & ~1;
+    return pl;
+}
+
+// P[frame][j][d] -> c->fftP; wp == nullptr: plain CAF of (ref, srv); else srv is cleaned on the fly with the taps
+// spectrum wp ([nf][L], same r3)
+int caf_fft(Ctx* c, const CafFftPlan& pl, const float2* ref, const float2* srv, long long n, Batch bt, int R, int F,
+            const float* win32, long long D, int c0, long long ntaps, const float2* wp, int M, int peek) {
+    const float2* tw;
+    TRY(fft_twiddles(c, pl.r3, &tw));
+    TRY(c->fftP.ensure((size_t)bt.nf * F * pl.HT * sizeof(float2)));
+    fftc::CafFftParams p{};
+    p.ref = ref; p.srv = srv; p.frame_stride = bt.stride; p.win = win32; p.wp = wp;
+    p.n = (int)n; p.R = R; p.F = F; p.M = M; p.peek = peek;
+    p.D = D; p.c0 = c0; p.ntaps = (int)ntaps; p.Bmax = pl.Bmax;
+    p.P = c->fftP.as<float2>(); p.HT = pl.HT; p.tw = tw;
+    const dim3 grid(F, bt.nf);
+    {
+        ProfScope ps(c, K_LAGCORR_CAF);
+        if (wp) { PRC_R3_SWITCH(pl.r3, (fftc::caf_fft_kernel<R3, true><<<grid, 16 * R3, fft_smem(R3), c->stream>>>(p))); }
+        else { PRC_R3_SWITCH(pl.r3, (fftc::caf_fft_kernel<R3, false><<<grid, 16 * R3, fft_smem(R3), c->stream>>>(p))); }
+    }
+    return check_launch("caf_fft_kernel");
+}
+
 // --------------------------------------------------------------------------- device pipelines
 // All pointers are device pointers; everything is enqueued on c->stream.
 
@@ -480,9 +682,12 @@ int decimator_offset(long long ntaps, long long D) {   // resample_poly alignmen
     return (int)(pre_remove * D - pre_pad);
 }
 
+// bt.nf > 1 (a batch of frames) and fuse_wp != nullptr (clutter filter applied inside the CAF kernel, taps spectrum
+// [nf][L] for the transform length of caf_fft_plan(..., fuse_M)) exist on the FFT-domain path only
 int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int R, int F,
                  const float* win32, const float* dtaps32, long long ndtaps, float2* out,
-                 bool refw_ready = false, bool caf_planes_ready = false) {
+                 bool refw_ready = false, bool caf_planes_ready = false, Batch bt = Batch{},
+                 const float2* fuse_wp = nullptr, int fuse_M = 0, int fuse_peek = 0) {
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
     if (F < 1 || R < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", F, R);
     const long long D = n / F;
@@ -506,8 +711,18 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     long long d_per_cta = 0;
     const float2* bnd_x = nullptr;                  // boundary-sample correction of the tensor-core path
     const float* bnd_w_all = nullptr;               // ... window to apply to bnd_x on the fly (bnd_x unweighted)
-    const CafTc ct = (ntaps == D + 1 && c0 == D / 2) ? caf_tc_plan(c, n, R, F, taps != nullptr) : CafTc{};
-    if (ct.on) {
+    const float2* dop_src = nullptr;                // Doppler-stage input when it is not c->partial
+    const CafFftPlan fp = caf_fft_plan(n, R, F, ntaps, D, taps == nullptr && ntaps == D + 1, fuse_wp ? fuse_M : 0);
+    if ((bt.nf > 1 || fuse_wp) && !fp.on)
+        return fail(PRC_E_INVALID, "batched / fused CAF needs the FFT-domain path (n=%lld, F=%d, R=%d not eligible)", n, F, R);
+    const CafTc ct = (!fp.on && ntaps == D + 1 && c0 == D / 2) ? caf_tc_plan(c, n, R, F, taps != nullptr) : CafTc{};
+    if (fp.on) {
+        // ---- FFT-domain block correlations (fftcorr.cuh): one CTA per Doppler block, P[j][d] straight from the channels
+        TRY(caf_fft(c, fp, ref, srv, n, bt, R, F, win32, D, c0, ntaps, fuse_wp, fuse_M, fuse_peek));
+        g.nchunk = 1;
+        g.HT = fp.HT;
+        dop_src = c->fftP.as<float2>();
+    } else if (ct.on) {
         // ---- tensor-core CAF: one (Doppler block, pass) item per accumulation, persistent CTAs
         // ref * window as complex64 is needed to build the x planes here; when the LS stage already wrote them
         // (caf_planes_ready) only the F boundary samples use it, and those are weighted on the fly
@@ -646,10 +861,12 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
         c->tw_F = F;
     }
     DopplerParams d{};
-    d.partial = c->partial.as<float2>();
+    d.partial = dop_src ? dop_src : c->partial.as<float2>();
     d.tw = c->tw.as<float2>();
     d.out = out;
     d.F = F; d.R = R; d.nchunk = g.nchunk; d.HT = g.HT;
+    d.partial_fstride = (long long)F * g.nchunk * g.HT;
+    d.out_fstride = (long long)F * (R + 1);
     d.blk_len = (int)ntaps; d.per_cta = d_per_cta;
     d.bx = bnd_x; d.bs = srv; d.bwin = bnd_x ? bnd_w_all : nullptr; d.bstride = D; d.boff = c0; d.n = (int)n;
     int logF = 0;
@@ -658,32 +875,36 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     const bool pow2 = (1 << logF) == F && F >= 2;
     ProfScope ps_doppler(c, K_DOPPLER);
     if (pow2 && F <= 8192) {
-        if (F <= 1024 && ceil_div(R + 1, 8) >= c->nsm) {
+        if (F <= 1024 && (long long)ceil_div(R + 1, 8) * bt.nf >= c->nsm) {
             const size_t sm = (size_t)2 * F * 8 * sizeof(float2);
-            doppler_fft_pow2_kernel<8><<<ceil_div(R + 1, 8), 256, sm, c->stream>>>(d);
+            doppler_fft_pow2_kernel<8><<<dim3(ceil_div(R + 1, 8), bt.nf), 256, sm, c->stream>>>(d);
         } else if (F <= 4096) {     // also the small-grid case: 2 columns per CTA fill more SMs
             const size_t sm = (size_t)2 * F * 2 * sizeof(float2);
-            doppler_fft_pow2_kernel<2><<<ceil_div(R + 1, 2), 256, sm, c->stream>>>(d);
+            doppler_fft_pow2_kernel<2><<<dim3(ceil_div(R + 1, 2), bt.nf), 256, sm, c->stream>>>(d);
         } else {
             const size_t sm = (size_t)2 * F * sizeof(float2);
-            doppler_fft_pow2_kernel<1><<<R + 1, 256, sm, c->stream>>>(d);
+            doppler_fft_pow2_kernel<1><<<dim3(R + 1, bt.nf), 256, sm, c->stream>>>(d);
         }
         TRY(check_launch("doppler_fft_pow2_kernel"));
     } else {
         TRY(c->pbuf.ensure((size_t)F * (R + 1) * sizeof(float2)));
-        chunk_sum_kernel<<<ceil_div((long long)F * (R + 1), 256), 256, 0, c->stream>>>(
-            c->partial.as<float2>(), c->pbuf.as<float2>(), F, R, g.nchunk, g.HT, (int)ntaps, d_per_cta, d);
-        TRY(check_launch("chunk_sum_kernel"));
-        doppler_dft_kernel<<<dim3(ceil_div(R + 1, 128), F), 128, 0, c->stream>>>(
-            c->pbuf.as<float2>(), c->tw.as<float2>(), out, F, R);
-        TRY(check_launch("doppler_dft_kernel"));
+        for (int fr = 0; fr < bt.nf; ++fr) {      // any F: chunk sum + direct DFT, frame by frame
+            chunk_sum_kernel<<<ceil_div((long long)F * (R + 1), 256), 256, 0, c->stream>>>(
+                d.partial + (size_t)fr * d.partial_fstride, c->pbuf.as<float2>(), F, R, g.nchunk, g.HT, (int)ntaps, d_per_cta, d);
+            TRY(check_launch("chunk_sum_kernel"));
+            doppler_dft_kernel<<<dim3(ceil_div(R + 1, 128), F), 128, 0, c->stream>>>(
+                c->pbuf.as<float2>(), c->tw.as<float2>(), out + (size_t)fr * d.out_fstride, F, R);
+            TRY(check_launch("doppler_dft_kernel"));
+        }
     }
     return PRC_OK;
 }
 
+// bt.nf > 1 (a batch of frames; taps_out then receives [nf][M]) and need_out == false (only the taps are wanted: the
+// caller applies them inside the CAF kernel) exist on the FFT-domain path only
 int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek,
               double reg, float2* out, float2* taps_out, const float* win32 = nullptr, bool* refw_ready = nullptr,
-              CafTc* caf = nullptr, bool linear = false) {
+              CafTc* caf = nullptr, bool linear = false, Batch bt = Batch{}, bool need_out = true) {
     // linear: LS_Filter_Toeplitz semantics -- correlations and FIR treat ref/srv as zero outside [0, n)
     if (refw_ready) *refw_ready = false;
     bool caf_x_done = false;
@@ -692,6 +913,18 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
         return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
     const int M = filter_len + peek;
     if (M > 2048) return fail(PRC_E_INVALID, "%d taps exceed the Toeplitz solver's maximum of 2048", M);
+    const LsFftPlan lf = ls_fft_plan(c, n, M, bt.nf);
+    if ((bt.nf > 1 || !need_out) && !lf.on)
+        return fail(PRC_E_INVALID, "batched LS filter needs the FFT-domain path (n=%lld, %d taps not eligible)", n, M);
+    if (lf.on) {
+        // ---- FFT-domain path (fftcorr.cuh): block spectra -> lag sums -> float64 Toeplitz solve -> overlap-save FIR
+        TRY(ls_fft_corr(c, lf, ref, srv, n, bt, M, peek, linear));
+        TRY(levinson_launch(c, lf.ncta, lf.HT, M, reg, bt.nf));
+        if (need_out) TRY(fir_fft(c, lf.r3, ref, srv, out, n, bt, M, peek, linear));
+        if (taps_out)
+            CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)bt.nf * M * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+        return PRC_OK;
+    }
     Geo g{};
     bool use_fir_tc = false;
     int lead = 0, fir_shift = 0, fir_kv = 0, fir_nblk = 0;
@@ -840,7 +1073,7 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
     lp.M = M;
     lp.reg = reg;
     lp.taps = c->lstaps.as<float2>();
-    lp.status = c->status.as<int>();
+    lp.status = c->status.as<int>() + c->status_slot;
     {
         ProfScope ps(c, K_LEVINSON);
         if (M <= 1024) levinson_kernel<1><<<1, 1024, levinson_smem(M, 1024), c->stream>>>(lp);
@@ -1168,12 +1401,48 @@ int finish(Ctx* c, unsigned flags) {
     return PRC_OK;
 }
 
-int check_ls_status(Ctx* c, unsigned flags) {
-    if (flags & PRC_FLAG_ASYNC) return PRC_OK;   // caller owns the synchronisation; status stays on the device
-    int st = 0;
-    CU(cudaMemcpyAsync(&st, c->status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+int check_ls_status(Ctx* c, unsigned flags, int nf = 1) {
+    if (flags & PRC_FLAG_ASYNC) return PRC_OK;   // caller owns the synchronisation; status stays on the device (prc_ls_status)
+    std::vector<int> st((size_t)nf, 0);
+    CU(cudaMemcpyAsync(st.data(), c->status.p, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (st != 0) return fail(PRC_E_SINGULAR, "LS normal equations are not positive definite (singular Gram matrix)");
+    for (int i = 0; i < nf; ++i)
+        if (st[i] != 0)
+            return fail(PRC_E_SINGULAR, "LS normal equations are not positive definite (singular Gram matrix, frame %d)", i);
+    return PRC_OK;
+}
+
+// one frame (or, on the FFT-domain path, a batch of frames) of  LS_Filter -> fast_xambg  on device pointers
+int frame_device(Ctx* c, const float2* ref, const float2* srv, long long n, Batch bt, int filter_len, int peek, double reg,
+                 int R, int F, const float* win32, float2* maps, float2* taps_out, float2* cleaned_out) {
+    const int M = filter_len + peek;
+    const long long D = n / F;
+    const LsFftPlan lf = (M >= 1 && M <= 2048) ? ls_fft_plan(c, n, M, bt.nf) : LsFftPlan{};
+    const CafFftPlan cf = (D >= 2) ? caf_fft_plan(n, R, F, D + 1, D, true, M) : CafFftPlan{};
+    if (lf.on && cf.on) {
+        // FFT-domain frame: lag sums -> Toeplitz solve -> taps spectrum -> CAF with the clutter filter applied to the
+        // surveillance spectrum inside the kernel (the cleaned channel exists only if the caller asks for it)
+        TRY(ls_device(c, ref, srv, n, filter_len, peek, reg, cleaned_out, taps_out, nullptr, nullptr, nullptr, false, bt,
+                      cleaned_out != nullptr));
+        TRY(taps_spectrum(c, cf.r3, M, bt.nf, &c->wp_caf));
+        return xambg_device(c, ref, srv, n, R, F, win32, nullptr, 0, maps, false, false, bt, c->wp_caf.as<float2>(), M, peek);
+    }
+    // direct-form kernels (tcgen05 / FP32), frame by frame
+    TRY(c->clean.ensure((size_t)n * sizeof(float2)));
+    TRY(c->status.ensure((size_t)bt.nf * sizeof(int)));
+    for (int fr = 0; fr < bt.nf; ++fr) {
+        const float2* r = ref + (size_t)fr * bt.stride;
+        const float2* sv = srv + (size_t)fr * bt.stride;
+        float2* dclean = cleaned_out ? cleaned_out + (size_t)fr * bt.stride : c->clean.as<float2>();
+        bool refw_ready = false;
+        CafTc caf = (n / F) % 2 == 0 ? caf_tc_plan(c, n, R, F, false) : CafTc{};
+        c->status_slot = fr;            // frame fr reports its Toeplitz-solve status in status[fr]
+        const int rc = ls_device(c, r, sv, n, filter_len, peek, reg, dclean, taps_out ? taps_out + (size_t)fr * M : nullptr, win32,
+                                 &refw_ready, &caf);
+        c->status_slot = 0;
+        TRY(rc);
+        TRY(xambg_device(c, r, dclean, n, R, F, win32, nullptr, 0, maps + (size_t)fr * F * (R + 1), refw_ready, caf.planes_ready));
+    }
     return PRC_OK;
 }
 
@@ -1410,51 +1679,104 @@ int prc_nlms_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_l
     return finish(c, flags);
 }
 
-int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek, float reg,
-                  int range_bins, int freq_bins, const void* window, prc_c64* out_map, prc_c64* taps_out,
-                  prc_c64* cleaned_out, int mem_kind, int device, void* stream, unsigned flags) {
-    if (!ref || !srv || !out_map) return fail(PRC_E_INVALID, "ref/srv/out_map must not be NULL");
+int prc_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                   int filter_len, int peek, float reg, int range_bins, int freq_bins, const void* window,
+                   prc_c64* out_maps, prc_c64* taps_out, prc_c64* cleaned_out, int mem_kind, int device, void* stream,
+                   unsigned flags) {
+    if (!ref || !srv || !out_maps) return fail(PRC_E_INVALID, "ref/srv/out_maps must not be NULL");
     if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
     if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (nframes < 1) return fail(PRC_E_INVALID, "nframes=%d invalid", nframes);
+    if (nframes > 1 && frame_stride < n) return fail(PRC_E_INVALID, "frame_stride=%lld smaller than n=%lld", (long long)frame_stride, (long long)n);
     if (freq_bins < 1 || range_bins < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", freq_bins, range_bins);
+    if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
+        return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
     Ctx* c;
     TRY(get_ctx(device, stream, &c));
     std::lock_guard<std::mutex> lk(c->mu);
+    const int M = filter_len + peek;
     const size_t nb = (size_t)n * sizeof(float2);
     const size_t ob = (size_t)freq_bins * (range_bins + 1) * sizeof(float2);
+    Batch bt;
+    bt.nf = nframes;
+    bt.stride = nframes > 1 ? frame_stride : n;
     const float2* dref = reinterpret_cast<const float2*>(ref);
     const float2* dsrv = reinterpret_cast<const float2*>(srv);
-    float2* dmap = reinterpret_cast<float2*>(out_map);
+    float2* dmap = reinterpret_cast<float2*>(out_maps);
     float2* dtaps = reinterpret_cast<float2*>(taps_out);
-    TRY(c->clean.ensure(nb));
-    float2* dclean = c->clean.as<float2>();
+    float2* dclean = reinterpret_cast<float2*>(cleaned_out);
     if (mem_kind == PRC_MEM_HOST) {
-        TRY(c->ref.ensure(nb));
-        TRY(c->srv.ensure(nb));
-        TRY(c->out.ensure(ob));
-        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        TRY(c->ref.ensure(nb * nframes));
+        TRY(c->srv.ensure(nb * nframes));
+        TRY(c->out.ensure(ob * nframes));
+        if (cleaned_out) TRY(c->clean.ensure(nb * nframes));
+        for (int fr = 0; fr < nframes; ++fr) {
+            CU(cudaMemcpyAsync(c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+        }
         dref = c->ref.as<float2>();
         dsrv = c->srv.as<float2>();
         dmap = c->out.as<float2>();
         dtaps = nullptr;
-    } else if (cleaned_out) {
-        dclean = reinterpret_cast<float2*>(cleaned_out);
+        dclean = cleaned_out ? c->clean.as<float2>() : nullptr;
+        bt.stride = n;
     }
     const float* win32;
     TRY(stage_window(c, window, n, mem_kind, flags, &win32));
-    bool refw_ready = false;
-    CafTc caf = (n / freq_bins) % 2 == 0 ? caf_tc_plan(c, n, range_bins, freq_bins, false) : CafTc{};
-    TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dclean, dtaps, win32, &refw_ready, &caf));
-    TRY(xambg_device(c, dref, dclean, n, range_bins, freq_bins, win32, nullptr, 0, dmap, refw_ready, caf.planes_ready));
+    TRY(frame_device(c, dref, dsrv, n, bt, filter_len, peek, (double)reg, range_bins, freq_bins, win32, dmap, dtaps, dclean));
     if (mem_kind == PRC_MEM_HOST) {
-        CU(cudaMemcpyAsync(out_map, c->out.p, ob, cudaMemcpyDeviceToHost, c->stream));
-        if (taps_out)
-            CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)(filter_len + peek) * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-        if (cleaned_out) CU(cudaMemcpyAsync(cleaned_out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(out_maps, c->out.p, ob * nframes, cudaMemcpyDeviceToHost, c->stream));
+        if (taps_out) {
+            if (nframes > 1 && !(ls_fft_plan(c, n, M, nframes).on && caf_fft_plan(n, range_bins, freq_bins, n / freq_bins + 1, n / freq_bins, true, M).on))
+                return fail(PRC_E_INVALID, "taps_out with host pointers and nframes > 1 needs the FFT-domain path");
+            CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)nframes * M * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (cleaned_out) {
+            const size_t fs = (size_t)(nframes > 1 ? frame_stride : n);
+            for (int fr = 0; fr < nframes; ++fr)
+                CU(cudaMemcpyAsync(cleaned_out + fr * fs, c->clean.as<float2>() + (size_t)fr * n, nb, cudaMemcpyDeviceToHost, c->stream));
+        }
     }
-    TRY(check_ls_status(c, flags));
+    TRY(check_ls_status(c, flags, nframes));
     return finish(c, flags);
+}
+
+int prc_frame_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek, float reg,
+                  int range_bins, int freq_bins, const void* window, prc_c64* out_map, prc_c64* taps_out,
+                  prc_c64* cleaned_out, int mem_kind, int device, void* stream, unsigned flags) {
+    return prc_frames_c64(ref, srv, n, 1, n, filter_len, peek, reg, range_bins, freq_bins, window, out_map, taps_out,
+                          cleaned_out, mem_kind, device, stream, flags);
+}
+
+int prc_ls_status(int device, void* stream, int* status, int nframes) {
+    if (!status || nframes < 1) return fail(PRC_E_INVALID, "status must not be NULL, nframes >= 1");
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->status.cap < (size_t)nframes * sizeof(int)) return fail(PRC_E_INVALID, "no LS solve of %d frames has run on this stream", nframes);
+    CU(cudaMemcpyAsync(status, c->status.p, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PRC_OK;
+}
+
+int prc_set_option(const char* name, int value) {
+    if (!name) return fail(PRC_E_INVALID, "name is NULL");
+    std::call_once(g_env_once, read_env);
+    const std::string k(name);
+    if (k == "fft") g_fft.store(value);
+    else if (k == "fft_min_n") g_fft_min_n.store(value);
+    else return fail(PRC_E_INVALID, "unknown option '%s'", name);
+    return PRC_OK;
+}
+
+int prc_get_option(const char* name, int* value) {
+    if (!name || !value) return fail(PRC_E_INVALID, "name/value is NULL");
+    std::call_once(g_env_once, read_env);
+    const std::string k(name);
+    if (k == "fft") *value = g_fft.load();
+    else if (k == "fft_min_n") *value = g_fft_min_n.load();
+    else return fail(PRC_E_INVALID, "unknown option '%s'", name);
+    return PRC_OK;
 }
 
 int prc_ls_toeplitz_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_len, int peek,

@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libprcore.so does not export {s}"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes table and header disagree"
-    assert lib.prc_version() == 100
+    assert lib.prc_version() == 200
 
 
 def test_signatures_match_reference():
