@@ -1,16 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- CPI frames/s of the passive-radar hot path (LS_Filter -> fast_xambg) on B200.
+"""bench.py -- CPI frames/s of the passive-radar hot path (clutter filter -> fast_xambg) on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU oracle port on host cores
+    python bench.py --gpus N --steps K --warmup W                     # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W    # the reference's CPU path on the host cores
+    python bench.py --config c4                                       # NLMS_filter -> fast_xambg, 2M-sample CPI, 512 x 400
+    python bench.py --config c5                                       # sweep CPI 256k..4M x Doppler 64..1024 (one line, "sweep": [...])
 
-One "step" = one batch of ``--batch`` CPI frames of BASELINE config 2 (2**20 samples, 256
-Doppler x 300 range, LS_Filter with filterLen = 300, reg = 1, peek = 10, Kaiser(5) window) pushed
-through the frame pipeline.  ``value`` = frames/s with the frames already resident in HBM (the
-batch is 268 MB, larger than the 126 MB L2, so no step finds its inputs cached); ``e2e`` = the
-same through ``FramePipeline.run_host`` with pinned HOST buffers, H2D of both channels and D2H of
-the map inside the timed region.  Rank r processes its own frames (weak scaling, no data-path
-collective); time = max over ranks.
+One "step" = ``--frames-per-step`` CPI frames pushed through the frame pipeline: the rank's resident set of
+``--resident`` DISTINCT frames (default 125 = BASELINE config 3's 1000-frame stream over 8 GPUs; 2.1 GB, far larger
+than the 126 MB L2, so no pass finds its inputs cached) is walked as many times as the step needs.  With the defaults
+the timed region is 20 steps x 4000 frames = a few seconds; the SM clocks in the line are sampled INSIDE it.
+``value`` = frames/s with the frames already resident in HBM; ``e2e`` = the same through
+``FramePipeline.run_host`` with pinned HOST buffers, H2D of both channels and D2H of the map inside the timed region;
+``e2e_dropin`` = the reference's own call signatures (LS_Filter -> fast_xambg on pageable numpy arrays) driven from a
+thread pool the way main.py's dask scheduler does.  Rank r processes its own frames (weak scaling, no data-path
+collective); time = max over ranks.  With N > 1 the line also carries ``config3_stream``: the 1000-frame stream held by
+rank 0 and staged to the other ranks over NCCL (double buffered against compute).
 """
 from __future__ import annotations
 
@@ -30,12 +35,17 @@ if ROOT not in sys.path:
 
 CONFIGS = {
     # BASELINE.json configs[1] / [2]: the configuration the metric is quoted on
-    "c2": dict(n=2 ** 20, F=256, R=300, filter_len=300, peek=10, reg=1.0,
+    "c2": dict(n=2 ** 20, F=256, R=300, filter_len=300, peek=10, reg=1.0, clutter="ls",
                name="1M-sample CPI (2^20), 256 Doppler x 300 range, LS_Filter(filterLen=300, reg=1, peek=10) -> fast_xambg(kaiser 5.0)"),
     # BASELINE.json configs[0]: the reference's CPU-runnable plumbing case
-    "c1": dict(n=200_000, F=64, R=100, filter_len=100, peek=10, reg=1.0,
+    "c1": dict(n=200_000, F=64, R=100, filter_len=100, peek=10, reg=1.0, clutter="ls",
                name="200k-sample CPI, 64 Doppler x 100 range, LS_Filter -> fast_xambg"),
+    # BASELINE.json configs[3]: NLMS clutter variant (block_len 1 = the reference's NLMS_filter; --nlms-block B = block_NLMS)
+    "c4": dict(n=2 ** 21, F=512, R=400, filter_len=400, peek=10, mu=0.05, clutter="nlms",
+               name="2M-sample CPI (2^21), 512 Doppler x 400 range, NLMS_filter(filterLen=400, mu=0.05, peek=10) -> fast_xambg(kaiser 5.0)"),
 }
+SWEEP_N = [2 ** 18, 2 ** 19, 2 ** 20, 2 ** 21, 2 ** 22]
+SWEEP_F = [64, 256, 1024]
 METRIC = "CPI frames/sec (1M-sample CPI, 256 Doppler x 300 range)"
 UNIT = "frames/s"
 
@@ -46,59 +56,44 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--batch", type=int, default=16, help="frames per step")
-    ap.add_argument("--slots", type=int, default=8, help="concurrent frame slots (CUDA streams)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["c5"])
+    ap.add_argument("--resident", type=int, default=0, help="distinct frames resident in HBM per GPU (0 = per config)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per step per GPU (0 = per config)")
+    ap.add_argument("--batch", type=int, default=16, help="frames per library call (one launch of each kernel)")
+    ap.add_argument("--slots", type=int, default=3, help="concurrent CUDA streams of the frame pipeline")
     ap.add_argument("--profile", default="P1", choices=["P0", "P1"])
+    ap.add_argument("--nlms-block", type=int, default=1, help="config c4: block_len of block_NLMS (1 = NLMS_filter)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="skip the config-3 NCCL staging measurement at N > 1")
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU arm (0 = auto)")
     return ap.parse_args()
 
 
-# ----------------------------------------------------------------------------- bytes / flops
+def config_dict(cfg, args, world):
+    """The `config` object of the JSON line -- identical on both arms."""
+    return {"workload": cfg["name"], "profile": args.profile, "n": cfg["n"], "doppler_bins": cfg["F"], "range_bins": cfg["R"],
+            "clutter_filter": "LS_Filter" if cfg["clutter"] == "ls" else ("NLMS_filter" if args.nlms_block == 1 else f"block_NLMS(blockLen={args.nlms_block})"),
+            "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"}
+
+
+# ----------------------------------------------------------------------------- bytes
 def bytes_frame(n, F, R):
     """Compulsory HBM bytes per frame: read ref+srv once, write the map once."""
     return 2 * 8 * n + 8 * F * (R + 1)
 
 
 def kernel_alg_bytes(cfg):
-    """Algorithmic bytes per launch for each kernel of the frame."""
+    """Algorithmic bytes per FRAME for each kernel of the frame."""
     n, F, R = cfg["n"], cfg["F"], cfg["R"]
     M = cfg["filter_len"] + cfg["peek"]
     return {
         "lagcorr_ls": 2 * 8 * n + 2 * 8 * M,        # read ref, srv; write 2 x M correlation lags
         "levinson": 2 * 8 * M + 8 * M,
         "fir_apply": 3 * 8 * n,                     # read ref, srv; write cleaned srv
-        "lagcorr_caf": 2 * 8 * n + 4 * n + 8 * F * (R + 1),   # ref, cleaned srv, f32 window; block sums
+        "lagcorr_caf": 2 * 8 * n + 4 * n + 8 * F * (R + 1),   # ref, srv, f32 window; block sums
         "doppler_fft": 2 * 8 * F * (R + 1),
+        "nlms": 3 * 8 * n,
     }
-
-
-def kernel_alg_flops(cfg):
-    """Algorithmic flops per launch: direct-form complex MACs (8 flop each), SURVEY.md 8d."""
-    n, F, R = cfg["n"], cfg["F"], cfg["R"]
-    M = cfg["filter_len"] + cfg["peek"]
-    return {"lagcorr_ls": 2 * 8 * n * M, "fir_apply": 8 * n * M, "lagcorr_caf": 8 * n * (R + 1)}
-
-
-def kernel_issued_flops(cfg):
-    """BF16 tensor-core flops the tcgen05 kernels actually issue per launch:
-    every product is evaluated as 6 BF16 MMAs (three-way split), the Toeplitz GEMMs compute a
-    128 x 256 tile per 64-lag group (toepcorr.cuh) and the FIR a 128 x 128 tile per 64 samples over
-    K = 2*(64 + M) padded to 64 (firtc.cuh).  Mirrors the geometry chosen in prcore.cu."""
-    n, F, R = cfg["n"], cfg["F"], cfg["R"]
-    M = cfg["filter_len"] + cfg["peek"]
-    ceil = lambda a, b: -(-a // b)
-    mma_toep = 2 * 128 * 256 * 16
-    nk = ceil(n, 1024)
-    out = {"lagcorr_ls": 2 * ceil(2 * (64 + M), 256) * nk * 6 * mma_toep}
-    D = n // F
-    if D % 1024 == 0:
-        out["lagcorr_caf"] = F * ceil(2 * (64 + R + 1), 256) * (D // 1024) * 6 * mma_toep
-    pre = max(0, ceil(M - 1 - cfg["peek"], 4) * 4)
-    kvp = ceil(2 * (64 + cfg["peek"] + pre), 64) * 64
-    out["fir_apply"] = ceil(ceil(n, 64), 128) * (kvp // 16) * 6 * (2 * 128 * 128 * 16)
-    return out
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -124,9 +119,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken in [t_begin, t_end] (perf_counter seconds); all samples when None."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -136,7 +132,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_begin is not None and not (t_begin <= ts <= t_end):
+                continue
             parts = [x.strip() for x in r.split(",")]
             if len(parts) < 7:
                 continue
@@ -152,66 +150,103 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(smax)) if smax else None,
                 "power_w_max": float(max(power)) if power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "sampled": "inside the timed region", "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------- CPU arm (oracle port)
-def _cpu_sample_worker(args):
-    """One bounded sample of the frame on the CPU oracle (TEST INFRASTRUCTURE used as the timed
-    CPU baseline): LS_Filter on n/ls_div samples with the full tap count, fast_xambg on the full
-    frame for nlag_sub of the R+1 lags.  Returns the estimated seconds for one whole frame."""
-    cfg, seed_frame, ls_div, nlag_sub, profile = args
-    import scipy.signal as signal
+# ----------------------------------------------------------------------------- CPU arm
+def _ref_modules():
+    """(LS_Filter, NLMS_filter, fast_xambg, kind): the UNMODIFIED reference functions from baseline/_ref when the
+    recipe baseline/install_ref.py has been run (kind "reference"), else the oracle port (kind "port")."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_dir, "passiveRadar")):
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+        from passiveRadar.clutter_removal import LS_Filter, NLMS_filter
+        from passiveRadar.range_doppler_processing import fast_xambg
+        return LS_Filter, NLMS_filter, fast_xambg, "reference"
     from oracle import clutter_oracle as co
     from oracle import xambg_oracle as xo
+    return co.ls_filter_oracle, co.nlms_filter_oracle, xo.fast_xambg_oracle, "port"
+
+
+def _install_decimate_shim():
+    """SciPy >= 1.12's decimate(ftype=dlti) detours through dlti._as_zpk() -> np.roots of degree n/F PER RANGE LAG
+    (46 s per lag at 4096) before doing the FIR it was asked for; route FIR dlti straight to resample_poly, which is
+    what decimate ends up calling -- bit-identical output (tests/test_oracle_golden.py::test_shim_is_bit_identical...).
+    This patches a SciPy function for the CPU arm; the reference's own code is untouched."""
+    import scipy.signal as signal
+    if getattr(signal.decimate, "_prc_shim", False):
+        return
+    real = signal.decimate
+
+    def patched(x, q, n=None, ftype='iir', axis=-1, zero_phase=True):
+        if isinstance(ftype, signal.dlti) and zero_phase:
+            tf = ftype._as_tf()
+            den = np.atleast_1d(tf.den)
+            if den.shape[0] == 1:
+                return signal.resample_poly(x, 1, q, axis=axis, window=tf.num / tf.den)
+        return real(x, q, n=n, ftype=ftype, axis=axis, zero_phase=zero_phase)
+
+    patched._prc_shim = True
+    signal.decimate = patched
+
+
+def _cpu_sample_worker(job):
+    """One bounded sample of a frame on the CPU: the clutter filter on n/div samples with the full tap count (its cost
+    is linear in n: data matrix, Gram and solve for LS_Filter, the recurrence for NLMS_filter) and fast_xambg on the
+    FULL frame with all range lags.  Returns (estimated seconds for one whole frame, filter seconds, xambg seconds)."""
+    cfg, seed_frame, div, profile, nlms_block = job
+    import scipy.signal as signal
     from passiveradar_b200 import synth
+    LS_Filter, NLMS_filter, fast_xambg, kind = _ref_modules()
+    _install_decimate_shim()
     n, F, R = cfg["n"], cfg["F"], cfg["R"]
     ref, srv = synth.make_frame(n, profile, seed_frame)
     w = signal.get_window(("kaiser", 5.0), n)
-    ns = n // ls_div
+    ns = n // div
     t0 = time.perf_counter()
-    co.ls_filter_oracle(ref[:ns], srv[:ns], cfg["filter_len"], cfg["reg"], cfg["peek"])
-    t_ls = time.perf_counter() - t0
+    if cfg["clutter"] == "ls":
+        LS_Filter(ref[:ns], srv[:ns], cfg["filter_len"], cfg["reg"], cfg["peek"])
+    else:
+        NLMS_filter(ref[:ns], srv[:ns], cfg["filter_len"], cfg["mu"], cfg["peek"])
+    t_f = time.perf_counter() - t0
     t0 = time.perf_counter()
-    xo.fast_xambg_oracle(ref, srv, nlag_sub - 1, F, n, w)
+    fast_xambg(ref, srv, R, F, n, w)
     t_x = time.perf_counter() - t0
-    return t_ls * ls_div + t_x * (R + 1) / nlag_sub, t_ls, t_x
+    return t_f * div + t_x, t_f, t_x
 
 
 class CpuArm:
-    """Frame-parallel pool, one process per host core (OPENBLAS_NUM_THREADS=1), as SURVEY 8d asks."""
+    """Frame-parallel pool, one process per host core (1 BLAS thread each), as SURVEY 8d asks."""
 
-    def __init__(self, cfg, procs, profile, rounds=1):
+    def __init__(self, cfg, procs, profile, nlms_block=1):
         import multiprocessing as mp
         self.cfg = cfg
         self.profile = profile
+        self.nlms_block = nlms_block
         ncpu = os.cpu_count() or 1
         try:
             ncpu = len(os.sched_getaffinity(0))
         except (AttributeError, OSError):
             pass
-        # bounded sample, sized so that `rounds` rounds finish in ~2 minutes (a round with the
-        # 1/16 sample takes ~10 s on 8 cores: page-fault bound 160 MB data matrices)
-        div = 16
-        while div < 256 and rounds * 160.0 / div > 120.0:
-            div *= 2
-        self.ls_div = div if cfg["n"] >= 2 ** 19 else 1
-        self.nlag_sub = max(1, (cfg["R"] + 1) // div) if cfg["n"] >= 2 ** 19 else cfg["R"] + 1
-        # ~1 GB per worker at the bounded sample; cap by cores and by memory
+        # bounded sample: LS_Filter at full size builds a 2.6 GB data matrix twice over (33-62 s, 8 GB RSS per frame);
+        # n/8 keeps a worker at ~1 GB and a few seconds.  NLMS_filter is a Python loop of 8.8 us per sample: n/32.
+        big = cfg["n"] >= 2 ** 19
+        self.div = (8 if cfg["clutter"] == "ls" else 32) if big else 1
         try:
             mem_gb = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
         except (ValueError, OSError):
             mem_gb = 16
-        self.procs = procs if procs > 0 else max(1, min(ncpu, int(mem_gb // 2), 64))
-        os.environ["OPENBLAS_NUM_THREADS"] = "1"
-        os.environ["OMP_NUM_THREADS"] = "1"
-        os.environ["MKL_NUM_THREADS"] = "1"
+        self.procs = procs if procs > 0 else max(1, min(ncpu, int(mem_gb // 3), 64))
+        for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[k] = "1"
+        self.kind = _ref_modules()[3]
         self.pool = mp.get_context("spawn").Pool(self.procs)
         self.round = 0
 
     def step(self):
-        """One round: every worker processes one bounded sample.  Returns (frames_equiv, seconds)."""
-        jobs = [(self.cfg, 1000 + self.round * self.procs + i, self.ls_div, self.nlag_sub, self.profile)
+        """One round: every worker processes one bounded sample.  Returns (frames/s, wall seconds, est s/frame)."""
+        jobs = [(self.cfg, 1000 + self.round * self.procs + i, self.div, self.profile, self.nlms_block)
                 for i in range(self.procs)]
         self.round += 1
         t0 = time.perf_counter()
@@ -219,18 +254,21 @@ class CpuArm:
         wall = time.perf_counter() - t0
         est = [r[0] for r in res]
         sampled = [r[1] + r[2] for r in res]
-        # whole-frame throughput of the pool = procs / (mean estimated whole-frame seconds), corrected
-        # by how much slower the round ran than its slowest worker's own compute (pool overhead)
+        # whole-frame throughput of the pool = procs / (mean estimated whole-frame seconds), corrected by how much
+        # slower the round ran than its slowest worker's own compute (pool overhead)
         eff = max(sampled) / wall if wall > 0 else 1.0
         fps = self.procs / float(np.mean(est)) * min(1.0, eff)
-        return fps, wall, float(np.mean(est))
+        return fps, wall, float(np.mean(est)), float(np.mean([r[1] for r in res])), float(np.mean([r[2] for r in res]))
 
     def sample_text(self):
         c = self.cfg
-        return (f"per worker: LS_Filter oracle on n/{self.ls_div}={c['n'] // self.ls_div} samples x {c['filter_len'] + c['peek']} taps "
-                f"(time x{self.ls_div}) + fast_xambg oracle (shimmed decimate) on the full {c['n']}-sample frame for "
-                f"{self.nlag_sub} of {c['R'] + 1} lags (time x{(c['R'] + 1) / self.nlag_sub:.2f}); {self.procs} workers in parallel, "
-                f"1 BLAS thread each")
+        flt = "LS_Filter" if c["clutter"] == "ls" else "NLMS_filter"
+        src = "the reference's own functions (baseline/_ref, unmodified)" if self.kind == "reference" else "the oracle port"
+        ext = (f"{flt} on n/{self.div} = {c['n'] // self.div} samples with all {c['filter_len'] + c['peek']} taps, time x{self.div} "
+               f"(EXTRAPOLATED: cost linear in n)") if self.div > 1 else f"{flt} on the full frame"
+        return (f"per worker, {src}: {ext} + fast_xambg on the FULL {c['n']}-sample frame, all {c['R'] + 1} range lags "
+                f"(measured, scipy.signal.decimate's np.roots detour bypassed bit-identically); {self.procs} workers in "
+                f"parallel, 1 BLAS thread each")
 
     def close(self):
         self.pool.terminate()
@@ -240,16 +278,14 @@ class CpuArm:
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    arm = CpuArm(cfg, args.cpu_procs, args.profile, rounds=args.steps + args.warmup)
+    arm = CpuArm(cfg, args.cpu_procs, args.profile, args.nlms_block)
     try:
         for _ in range(args.warmup):
             arm.step()
-        fps_list, wall = [], 0.0
+        fps_list = []
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            fps, w, _ = arm.step()
-            fps_list.append(fps)
-            wall += w
+            fps_list.append(arm.step()[0])
         total = time.perf_counter() - t0
     finally:
         arm.close()
@@ -258,21 +294,120 @@ def run_reference(args, cfg, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; f64 block sums)",
-        "data": "synthetic", "config": {"workload": cfg["name"], "profile": args.profile},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": "port",
-                         "sample": arm.sample_text()},
+        "data": "synthetic", "config": config_dict(cfg, args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": arm.kind,
+                         "sample": arm.sample_text(), "filter_extrapolated": arm.div > 1},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# ----------------------------------------------------------------------------- GPU arm
-def run_b200(args, cfg, rank, world, local_rank):
+# ----------------------------------------------------------------------------- GPU arm helpers
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)),
+                "source": "MEASURED_PEAKS.json (measured copy bandwidth)", "of": "of measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)", "of": "of fallback"}
+
+
+def make_resident(torch, dev, n, profile, count, rank, base=8):
+    """`count` DISTINCT frames on the device: `base` frames from the seeded host generator (the ones the parity tests
+    use), the rest derived on the device by a circular roll of both channels (different per frame) and a unit phasor --
+    same statistics, same clutter geometry (the LS model is circular), different samples."""
+    from passiveradar_b200 import synth
+    base = min(base, count)
+    refs, srvs = zip(*[synth.make_frame(n, profile, rank * 1000 + i) for i in range(base)])
+    bref = torch.from_numpy(np.stack(refs)).to(dev)
+    bsrv = torch.from_numpy(np.stack(srvs)).to(dev)
+    ref_d = torch.empty((count, n), dtype=torch.complex64, device=dev)
+    srv_d = torch.empty((count, n), dtype=torch.complex64, device=dev)
+    for i in range(count):
+        k, g = i % base, i // base
+        if g == 0:
+            ref_d[i] = bref[k]
+            srv_d[i] = bsrv[k]
+        else:
+            ph = complex(np.exp(2j * np.pi * (0.137 * g + 0.011 * k)))
+            sh = (7919 * g + 104729 * k) % n
+            ref_d[i] = torch.roll(bref[k], sh) * ph
+            srv_d[i] = torch.roll(bsrv[k], sh) * ph
+    return ref_d, srv_d, np.stack(refs), np.stack(srvs)
+
+
+class Workload:
+    """What one step runs, per config: c2/c1 the fused LS frame pipeline; c4 NLMS_filter (one CTA per frame, the batch
+    fills the GPU) followed by the batched CAF of the cleaned channels."""
+
+    def __init__(self, args, cfg, torch, dev, local_rank):
+        from passiveradar_b200 import _lib
+        from passiveradar_b200.frames import FramePipeline
+        self.args, self.cfg, self.torch, self.dev = args, cfg, torch, dev
+        self.lib = _lib.load()
+        self._lib = _lib
+        n, F, R = cfg["n"], cfg["F"], cfg["R"]
+        self.n, self.F, self.R = n, F, R
+        self.local_rank = local_rank
+        if cfg["clutter"] == "ls":
+            self.pipe = FramePipeline(n, R, F, filter_len=cfg["filter_len"], reg=cfg["reg"], peek=cfg["peek"],
+                                      window=("kaiser", 5.0), device=local_rank, nslots=args.slots, batch=args.batch)
+        else:
+            import scipy.signal as signal
+            self.window = torch.from_numpy(signal.get_window(("kaiser", 5.0), n).astype(np.float32)).to(dev)
+            self.clean = None
+            self.stream = torch.cuda.Stream(device=dev)       # the library keeps one workspace per caller stream
+
+    def run_device(self, ref_d, srv_d, maps_d):
+        if self.cfg["clutter"] == "ls":
+            self.pipe.run_device(ref_d, srv_d, maps_d)
+            return
+        torch, _lib, c = self.torch, self._lib, self.cfg
+        nf = ref_d.shape[0]
+        if self.clean is None or self.clean.shape[0] < nf:
+            self.clean = torch.empty((nf, self.n), dtype=torch.complex64, device=self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        self.stream.wait_stream(cur)
+        st = self.stream.cuda_stream
+        flags = _lib.FLAG_ASYNC | _lib.FLAG_WINDOW_F32
+        _lib.check(self.lib.prc_nlms_frames_c64(ref_d.data_ptr(), srv_d.data_ptr(), self.n, nf, ref_d.stride(0) if nf > 1 else self.n,
+                                                c["filter_len"], c["peek"], c["mu"], self.args.nlms_block, None,
+                                                self.clean.data_ptr(), None, _lib.MEM_DEVICE, self.local_rank, st, _lib.FLAG_ASYNC))
+        _lib.check(self.lib.prc_xambg_frames_c64(ref_d.data_ptr(), self.clean.data_ptr(), self.n, nf, self.n, self.R, self.F,
+                                                 self.window.data_ptr(), maps_d.data_ptr(), _lib.MEM_DEVICE, self.local_rank, st, flags))
+        cur.wait_stream(self.stream)
+
+    def run_host(self, ref_h, srv_h, maps_h, stage):
+        if self.cfg["clutter"] == "ls":
+            self.pipe.run_host(ref_h, srv_h, maps_h)
+            return
+        torch = self.torch
+        rd, sd, md = stage
+        nf = ref_h.shape[0]
+        rd[:nf].copy_(torch.from_numpy(ref_h), non_blocking=True)
+        sd[:nf].copy_(torch.from_numpy(srv_h), non_blocking=True)
+        self.run_device(rd[:nf], sd[:nf], md[:nf])
+        torch.from_numpy(maps_h.reshape(nf, self.F, self.R + 1)).copy_(md[:nf], non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+
+
+def time_passes(torch, dev, work, ref_d, srv_d, maps_d, frames):
+    """Walk the resident set until `frames` frames have been processed (enqueue only)."""
+    res = ref_d.shape[0]
+    done = 0
+    while done < frames:
+        m = min(res, frames - done)
+        work.run_device(ref_d[:m], srv_d[:m], maps_d[:m])
+        done += m
+
+
+def run_b200(args, cfg, rank, world, local_rank, quiet=False):
     import torch
     import torch.distributed as dist
-    from passiveradar_b200 import _lib, synth
-    from passiveradar_b200.frames import FramePipeline, pinned_empty
+    from passiveradar_b200 import _lib
+    from passiveradar_b200.frames import pinned_empty
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: libprcore has no CPU fallback")
@@ -282,21 +417,13 @@ def run_b200(args, cfg, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     n, F, R = cfg["n"], cfg["F"], cfg["R"]
-    B = args.batch
-    pipe = FramePipeline(n, R, F, filter_len=cfg["filter_len"], reg=cfg["reg"], peek=cfg["peek"],
-                         window=("kaiser", 5.0), device=local_rank, nslots=args.slots)
-
-    # synthetic frames (host, pinned) -- rank r owns frames r*B .. r*B+B-1 of the stream
-    ref_h = pinned_empty((B, n))
-    srv_h = pinned_empty((B, n))
-    for i in range(B):
-        r, s = synth.make_frame(n, args.profile, rank * B + i)
-        ref_h[i] = r
-        srv_h[i] = s
-    ref_d = torch.from_numpy(ref_h).to(dev)
-    srv_d = torch.from_numpy(srv_h).to(dev)
-    maps_d = torch.empty((B, F, R + 1), dtype=torch.complex64, device=dev)
-    maps_h = pinned_empty((B, F, R + 1, 1))
+    nlms = cfg["clutter"] == "nlms"
+    resident = args.resident or (296 if nlms else 125)
+    fps_guess = 450.0 if nlms else 25000.0
+    frames_per_step = args.frames_per_step or (resident if nlms else 4000)
+    work = Workload(args, cfg, torch, dev, local_rank)
+    ref_d, srv_d, ref_base, srv_base = make_resident(torch, dev, n, args.profile, resident, rank)
+    maps_d = torch.empty((resident, F, R + 1), dtype=torch.complex64, device=dev)
 
     def barrier():
         if world > 1:
@@ -311,45 +438,79 @@ def run_b200(args, cfg, rank, world, local_rank):
         return float(t.item())
 
     # ---- device-resident throughput (headline `value`)
-    for _ in range(max(args.warmup, 3)):
-        pipe.run_device(ref_d, srv_d, maps_d)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        time_passes(torch, dev, work, ref_d, srv_d, maps_d, min(frames_per_step, 2 * resident))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.25)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        pipe.run_device(ref_d, srv_d, maps_d)
+        time_passes(torch, dev, work, ref_d, srv_d, maps_d, frames_per_step)
     e1.record()
     barrier()
+    t_end = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - launches0
-    # nvidia-smi samples every 100 ms: when the timed region is shorter than that, keep the SAME
-    # workload running (untimed) until the sampler has seen at least ~0.6 s of it
-    t_load = time.perf_counter()
-    while rank == 0 and ms < 600.0 and time.perf_counter() - t_load < 0.6:
-        pipe.run_device(ref_d, srv_d, maps_d)
-        torch.cuda.synchronize(dev)
-    clocks = sampler.stop() if rank == 0 else None
-    barrier()
-    frames_total = B * args.steps * world
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    frames_total = frames_per_step * args.steps * world
     value = frames_total / (ms * 1e-3)
 
     # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
+    nb_host = ref_base.shape[0]
+    ref_h = pinned_empty((nb_host, n))
+    srv_h = pinned_empty((nb_host, n))
+    ref_h[:] = ref_base
+    srv_h[:] = srv_base
+    maps_h = pinned_empty((nb_host, F, R + 1, 1))
+    stage = None
+    if nlms:
+        stage = (torch.empty((nb_host, n), dtype=torch.complex64, device=dev), torch.empty((nb_host, n), dtype=torch.complex64, device=dev),
+                 torch.empty((nb_host, F, R + 1), dtype=torch.complex64, device=dev))
+    e2e_frames_per_step = max(nb_host, int(round((24 if nlms else 640) / nb_host)) * nb_host)
+    passes = e2e_frames_per_step // nb_host
     for _ in range(2):
-        pipe.run_host(ref_h, srv_h, maps_h)
+        work.run_host(ref_h, srv_h, maps_h, stage)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pipe.run_host(ref_h, srv_h, maps_h)      # synchronises its streams before returning
+        for _ in range(passes):
+            work.run_host(ref_h, srv_h, maps_h, stage)      # synchronises before returning
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = frames_total / e2e_s
+    e2e_total = e2e_frames_per_step * args.steps * world
+    e2e_value = e2e_total / e2e_s
 
-    # ---- what the host link can carry: plain pinned-memory H2D copies of the same 256 MiB, nothing else running
-    # (context for e2e, which moves 16.8 MB per frame over PCIe)
+    # ---- the reference's own call signatures from a thread pool (main.py:169-194 under dask's threaded scheduler):
+    # pageable numpy arrays in, numpy arrays out, one library workspace per calling thread
+    dropin = None
+    if rank == 0 and not nlms:
+        import concurrent.futures as cf
+        import scipy.signal as signal
+        import passiveradar_b200 as prb
+        w64 = signal.get_window(("kaiser", 5.0), n)
+        pairs = [(np.array(ref_base[i % nb_host]), np.array(srv_base[i % nb_host])) for i in range(8)]
+
+        def one(i):
+            r, s = pairs[i % 8]
+            cleaned = prb.LS_Filter(r, s, cfg["filter_len"], cfg["reg"], cfg["peek"])
+            return prb.fast_xambg(r, cleaned, R, F, n, w64)
+
+        nthr, ncall = 8, 48
+        with cf.ThreadPoolExecutor(nthr) as ex:
+            list(ex.map(one, range(nthr)))
+            t0 = time.perf_counter()
+            list(ex.map(one, range(ncall)))
+            dt = time.perf_counter() - t0
+        dropin = {"value": ncall / dt, "unit": UNIT, "threads": nthr, "calls": ncall,
+                  "api": "passiveradar_b200.LS_Filter -> passiveradar_b200.fast_xambg (reference signatures, pageable numpy in/out, float64 window)"}
+
+    # ---- what the host link can carry: plain pinned-memory H2D copies of the same buffers, nothing else running
     h2d_peak = None
     try:
         if rank == 0:
@@ -368,124 +529,176 @@ def run_b200(args, cfg, rank, world, local_rank):
     except Exception:       # context only: never let it break the bench line
         h2d_peak = None
 
-    # ---- per-kernel durations: CUDA events on the launching stream, one frame at a time on one stream
-    roofline = None
-    per_kernel = {}
+    # ---- per-kernel durations (CUDA events on the launching stream around every launch, one stream, the same batch
+    # size as the timed region, walking the resident set: inputs > L2) and single-frame latency
+    roofline, per_kernel, latency_us = None, {}, None
     if rank == 0:
-        single = FramePipeline(n, R, F, filter_len=cfg["filter_len"], reg=cfg["reg"], peek=cfg["peek"],
-                               window=("kaiser", 5.0), device=local_rank, nslots=1)
-        single.run_device(ref_d[:2], srv_d[:2], maps_d[:2])
+        peaks = load_peaks()
+        args1 = argparse.Namespace(**vars(args))
+        args1.slots = 1
+        single = Workload(args1, cfg, torch, dev, local_rank)
+        m = min(resident, 4 * args.batch) if not nlms else resident
+        single.run_device(ref_d[:m], srv_d[:m], maps_d[:m])
         torch.cuda.synchronize(dev)
         _lib.profile_reset()
         _lib.profile(True)
-        reps = max(1, min(4, args.steps))
-        for _ in range(reps):
-            single.run_device(ref_d, srv_d, maps_d)     # B frames back to back, inputs > L2
+        reps = 2 if nlms else 8
+        for r in range(reps):
+            o = (r * m) % max(1, resident - m + 1)
+            single.run_device(ref_d[o:o + m], srv_d[o:o + m], maps_d[o:o + m])
         torch.cuda.synchronize(dev)
         prof = _lib.profile_read()
         _lib.profile(False)
-        peaks = load_peaks()
+        frames_prof = reps * m
         algb = kernel_alg_bytes(cfg)
-        algf = kernel_alg_flops(cfg)
         tot = sum(v[0] for v in prof.values())
         for name, (tms, cnt) in prof.items():
             if cnt == 0:
                 continue
-            avg_us = 1e3 * tms / cnt
-            per_kernel[name] = {"avg_us": round(avg_us, 3), "launches": cnt, "share": round(tms / tot, 4) if tot else None,
-                                "alg_GBps": round(algb.get(name, 0) / (avg_us * 1e-6) / 1e9, 2) if name in algb else None,
-                                "alg_TFLOPs": round(algf[name] / (avg_us * 1e-6) / 1e12, 2) if name in algf else None}
-        # dominant kernel = largest share of SM-time; the Toeplitz solve is a single CTA (one SM of
-        # 148, latency-bound, hidden behind the other frames' kernels) and is not a roofline subject
-        dom = max((k for k in per_kernel if k in algb and k != "levinson"), key=lambda k: prof[k][0])
-        ach = per_kernel[dom]["alg_GBps"]
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if args.config == "c2" and os.path.exists(tpath):
+            us_frame = 1e3 * tms / frames_prof
+            per_kernel[name] = {"us_per_frame": round(us_frame, 3), "avg_launch_us": round(1e3 * tms / cnt, 2), "launches": cnt,
+                                "frames_per_launch": round(frames_prof / cnt, 2), "share": round(tms / tot, 4) if tot else None,
+                                "alg_GBps": round(algb[name] / (us_frame * 1e-6) / 1e9, 1) if name in algb else None}
+        # dominant kernel = largest share of the serialised kernel time, whatever it is
+        dom = max(per_kernel, key=lambda k: prof[k][0])
+        fpl = per_kernel[dom]["frames_per_launch"]
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(dom)      # dram read+write bytes per launch from the ncu --set full capture
-        tensor = os.environ.get("PRC_TC", "1") != "0" and dom in ("lagcorr_ls", "lagcorr_caf", "fir_apply")
-        fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e-6          # FFMA: 128 lanes x 2 flop x SMs x clock
-        common = {"traffic": traffic, "avg_launch_us": per_kernel[dom]["avg_us"],
-                  "alg_GBps": ach, "hbm_peak_GBps": peaks["hbm_gbs"],
-                  "alg_TFLOPs": per_kernel[dom]["alg_TFLOPs"], "fp32_pipe_peak_TFLOPs": round(fp32_peak, 1),
-                  "frame_GBps": round(bytes_frame(n, F, R) * value / world / 1e9, 2),
-                  "peak_source": peaks["source"]}
-        if tensor:
-            issued = kernel_issued_flops(cfg).get(dom)
-            issued_tf = issued / (per_kernel[dom]["avg_us"] * 1e-6) / 1e12 if issued else None
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": per_kernel[dom]["alg_TFLOPs"],
-                        "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": round(per_kernel[dom]["alg_TFLOPs"] / peaks["bf16_tflops_sustained"], 5),
-                        "issued_bf16_TFLOPs": round(issued_tf, 1) if issued_tf else None,
-                        "issued_frac": round(issued_tf / peaks["bf16_tflops_sustained"], 4) if issued_tf else None,
-                        "note": "algorithmic flops = direct-form complex MACs (8 flop); the kernel issues 6 BF16 MMAs per "
-                                "product (fp32-accurate three-way split) on Toeplitz-expanded tiles, so `issued` is what the "
-                                "tensor pipe actually sustains; the same algorithmic work on the FP32 pipe is capped at "
-                                "fp32_pipe_peak_TFLOPs. 145+ flop/B: not HBM bound (DESIGN.md section 4)", **common}
-        else:
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": round(ach / peaks["hbm_gbs"], 5),
-                        "fp32_frac_of_peak": (round(per_kernel[dom]["alg_TFLOPs"] / fp32_peak, 4)
-                                              if per_kernel[dom]["alg_TFLOPs"] is not None else None), **common}
+                tj = json.load(f)
+            ent = tj.get(args.config, {}).get(dom)
+            if ent:
+                traffic = ent["dram_bytes_per_frame"] * fpl
+                traffic_note = ent.get("note")
+        ach = per_kernel[dom]["alg_GBps"]
+        frame_gbps = bytes_frame(n, F, R) * value / world / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / peaks["hbm_gbs"], 5) if ach else None, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": algb.get(dom, 0) * fpl, "avg_launch_us": per_kernel[dom]["avg_launch_us"],
+                    "frames_per_launch": fpl, "traffic_note": traffic_note,
+                    "frame_GBps": round(frame_gbps, 1), "frame_frac": round(frame_gbps / peaks["hbm_gbs"], 5),
+                    "note": "frac: the dominant kernel's algorithmic bytes over its CUDA-event duration (timed inside a run of back-to-back "
+                            "launches) against the measured HBM copy bandwidth; frame_frac: the whole frame's compulsory bytes "
+                            "(2*8*n + 8*F*(R+1)) x the headline frames/s against the same peak. Kernels named by stage: lagcorr_ls = "
+                            "LS lag sums, levinson = float64 Toeplitz solve (one CTA per frame, latency-bound), lagcorr_caf = CAF block "
+                            "sums (clutter filter fused in), doppler_fft, misc = taps spectrum.",
+                    "peak_source": peaks["source"] + ", " + peaks["of"],
+                    "path": "fft" if _lib.get_option("fft") else "direct (tcgen05 / FP32)"}
+        # single-frame latency: one frame, one stream, synchronised
+        if not nlms:
+            lat = Workload(args1, cfg, torch, dev, local_rank)
+            lat.pipe.batch = 1
+            for _ in range(3):
+                lat.run_device(ref_d[:1], srv_d[:1], maps_d[:1])
+            torch.cuda.synchronize(dev)
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for i in range(20):
+                lat.run_device(ref_d[i:i + 1], srv_d[i:i + 1], maps_d[i:i + 1])
+            l1.record()
+            torch.cuda.synchronize(dev)
+            latency_us = round(1e3 * l0.elapsed_time(l1) / 20, 1)
+
+    # ---- config 3: the 1000-frame stream held by rank 0, staged over NCCL, double buffered against compute
+    stream = None
+    if world > 1 and not args.no_stream and not nlms:
+        from passiveradar_b200 import distributed as pd
+        stream = pd.stream_benchmark(work.pipe, ref_d, srv_d, maps_d, nframes_total=1000, chunk=args.batch, rank=rank, world=world,
+                                     device=dev)
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        arm = CpuArm(cfg, args.cpu_procs, args.profile)
+        arm = CpuArm(cfg, args.cpu_procs, args.profile, args.nlms_block)
         try:
-            fps, wall, est = arm.step()
-            cpu = {"value": fps, "unit": UNIT, "cores": arm.procs, "kind": "port", "sample": arm.sample_text(),
-                   "est_seconds_per_frame_per_core": est, "wall_s": wall}
+            fps, wall, est, t_f, t_x = arm.step()
+            cpu = {"value": fps, "unit": UNIT, "cores": arm.procs, "kind": arm.kind, "sample": arm.sample_text(),
+                   "est_seconds_per_frame_per_core": est, "filter_seconds_sampled": t_f, "xambg_seconds_full_frame": t_x,
+                   "filter_extrapolated": arm.div > 1, "wall_s": wall}
         finally:
             arm.close()
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; heavy sums as fp32-accurate BF16x3 tensor-core products with fp32 accumulation; f64 Toeplitz solve)", "data": "synthetic",
-            "config": {"workload": cfg["name"], "frames_per_step_per_gpu": B, "slots": args.slots,
-                       "profile": args.profile, "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                       "cache": f"inputs {B * 2 * n * 8 / 2 ** 20:.0f} MiB per step > 126 MB L2 (no flush needed)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 2 * n * 8,
-                    "d2h_bytes_per_step": B * F * (R + 1) * 8,
-                    "api": "passiveradar_b200.frames.FramePipeline.run_host (pinned host ndarrays)",
-                    "h2d_GBps": round(B * 2 * n * 8 * args.steps * world / e2e_s / 1e9 / world, 2),
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "c64 (f32 pairs: FP32 FFT-domain block correlations; f64 Toeplitz solve)" if not nlms else "c64 (f32 pairs)",
+            "data": "synthetic", "config": config_dict(cfg, args, world),
+            "run": {"frames_per_step_per_gpu": frames_per_step, "resident_distinct_frames_per_gpu": resident,
+                    "frames_per_call": args.batch, "slots": args.slots, "timed_region_s": round(ms * 1e-3, 3),
+                    "cache": f"resident set {resident * 2 * n * 8 / 2 ** 20:.0f} MiB per GPU > 126 MB L2 (no flush needed)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_frames_per_step * 2 * n * 8,
+                    "d2h_bytes_per_step": e2e_frames_per_step * F * (R + 1) * 8, "frames_per_step_per_gpu": e2e_frames_per_step,
+                    "api": "passiveradar_b200.frames.FramePipeline.run_host (pinned host ndarrays)" if not nlms else
+                           "prc_nlms_frames_c64 + prc_xambg_frames_c64 around pinned host ndarrays",
+                    "h2d_GBps": round(e2e_frames_per_step * 2 * n * 8 * args.steps / e2e_s / 1e9, 2),
                     "h2d_link_GBps": round(h2d_peak, 2) if h2d_peak else None,
                     "note": "h2d_GBps = input bytes per second per GPU through the timed region; h2d_link_GBps = plain "
                             "pinned-memory cudaMemcpy of the same buffers measured beside it (the PCIe ceiling of e2e)"},
+            "e2e_dropin": dropin,
+            "latency_us": latency_us,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
             "kernels": per_kernel,
+            "config3_stream": stream,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        if not quiet:
+            print(json.dumps(line), flush=True)
+    if world > 1 and not quiet:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE config 5: CPI 256k -> 4M samples x Doppler 64 -> 1024, LS frame, distinct frames, HBM GB/s vs roofline."""
+    import torch
+    import torch.distributed as dist
+    rows = []
+    base_steps = args.steps
+    for n in SWEEP_N:
+        for F in SWEEP_F:
+            cfg = dict(n=n, F=F, R=300, filter_len=300, peek=10, reg=1.0, clutter="ls", name=f"sweep n={n} F={F} R=300")
+            a = argparse.Namespace(**vars(args))
+            a.resident = max(16, min(125, (2 ** 31) // (16 * n)))
+            a.frames_per_step = max(a.resident, int(40000 * 2 ** 20 / n / max(base_steps, 1) / 10))
+            a.no_cpu_baseline = True
+            a.no_stream = True
+            line = run_b200(a, cfg, rank, world, local_rank, quiet=True)
+            if rank == 0:
+                rows.append({"n": n, "F": F, "R": 300, "frames_per_s": round(line["value"], 1),
+                             "frame_GBps": line["roofline"]["frame_GBps"], "frame_frac": line["roofline"]["frame_frac"],
+                             "e2e_frames_per_s": round(line["e2e"]["value"], 1), "latency_us": line["latency_us"],
+                             "dominant": line["roofline"]["kernel"]})
+            torch.cuda.empty_cache()
+    if rank == 0:
+        c2 = [r for r in rows if r["n"] == 2 ** 20 and r["F"] == 256][0]
+        out = {"metric": METRIC, "value": c2["frames_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+               "config": {"workload": "sweep CPI 256k..4M samples x Doppler 64..1024 (R=300, LS_Filter(300) -> fast_xambg); value = the n=2^20, F=256 row",
+                          "profile": args.profile}, "sweep": rows}
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def load_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            p = json.load(f)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops", 1718.7)),
-                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1453.0))),
-                "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)),
-                "source": "MEASURED_PEAKS.json (measured copy bandwidth / sustained cuBLAS bf16, kernel timed inside a long step)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1700.0, "bf16_tflops_sustained": 1450.0, "sm_max_mhz": 1965.0,
-            "source": "fallback (B200_PROFILING.md)"}
-
-
 def main():
     args = parse_args()
-    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config == "c5":
+        if args.impl == "reference":
+            raise SystemExit("the sweep has no CPU arm")
+        run_sweep(args, rank, world, local_rank)
+        return
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg, rank, world)
         return

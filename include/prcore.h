@@ -165,6 +165,20 @@ int prc_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframe
                    int mem_kind, int device, void* stream, unsigned flags);
 int prc_ls_status(int device, void* stream, int* status, int nframes);
 
+/* The other two operators of the path on nframes independent frames per call (same layout rules as prc_frames_c64):
+ * prc_nlms_frames_c64 -- NLMS_filter / block_NLMS (clutter_removal.py:189-249): the recurrence of one frame is serial,
+ *   so every frame gets its own CTA (one SM) and the batch fills the GPU; init_taps (filter_len + peek taps or NULL)
+ *   is shared by all frames, taps_out receives nframes * (filter_len + peek) taps.
+ * prc_xambg_frames_c64 -- fast_xambg (range_doppler_processing.py:12-90, default boxcar decimator) with one window for
+ *   all frames; out receives nframes maps of freq_bins x (range_bins + 1).
+ */
+int prc_nlms_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                        int filter_len, int peek, float mu, int block_len, const prc_c64* init_taps,
+                        prc_c64* out, prc_c64* taps_out, int mem_kind, int device, void* stream, unsigned flags);
+int prc_xambg_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                         int range_bins, int freq_bins, const void* window, prc_c64* out,
+                         int mem_kind, int device, void* stream, unsigned flags);
+
 /* ---- run-time switches (also read once from the environment: PRC_FFT, PRC_FFT_MIN_N) ----------------
  *   "fft"        1 (default): LS correlations, clutter FIR and CAF block sums as FFT-domain block correlations
  *                (csrc/fftcorr.cuh);  0: direct form on tcgen05 / FP32 (csrc/toepcorr.cuh, firtc.cuh, lagstream.cuh)

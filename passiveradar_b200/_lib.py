@@ -62,6 +62,10 @@ SIGNATURES = {
                                 C.c_void_p, _c64p, _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_frames_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                  C.c_void_p, _c64p, _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_nlms_frames_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int,
+                                      _c64p, _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_xambg_frames_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, _c64p,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_ls_status": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int]),
     "prc_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "prc_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),

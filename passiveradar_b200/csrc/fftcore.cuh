@@ -221,6 +221,18 @@ __device__ __forceinline__ void fft_n2p(float2 (&v)[16], int t, const Smem<R3>& 
     n2p_pass3<R3>(v, t, s.eb);
 }
 
+// same, with `after_pass1()` run once the group's first barrier has passed (every register of v has been consumed by
+// then): the place to start asynchronous copies that overwrite the shared-memory slots v was fetched from
+template <int R3, class Hook>
+__device__ __forceinline__ void fft_n2p(float2 (&v)[16], int t, const Smem<R3>& s, Hook after_pass1) {
+    n2p_pass1<R3>(v, t, s.ea, s.tw1);
+    __syncthreads();
+    after_pass1();
+    n2p_pass2<R3>(v, t, s.ea, s.eb, s.tw2);
+    __syncthreads();
+    n2p_pass3<R3>(v, t, s.eb);
+}
+
 template <int R3>
 __device__ __forceinline__ void fft_p2n(float2 (&v)[16], int t, const Smem<R3>& s) {
     p2n_pass1<R3>(v, t, s.eb);

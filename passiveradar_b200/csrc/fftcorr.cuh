@@ -17,8 +17,11 @@
 //                       wrap lands in the part of the segment no lag 0..R touches).  Segments of <= L - R - (M-1)
 //                       samples; spectra X conj(S_clean) accumulated per Doppler block; one transform back.
 //
-// All kernels take a batch of frames in gridDim.y (frame_stride samples apart).  Algebra pinned on the CPU by
-// scripts/fft/model.py (numpy) and scripts/fft/emul.cu (thread-by-thread run of fftcore.cuh).
+// All kernels take a batch of frames in gridDim.y (frame_stride samples apart).  Every hot loop has ONE transform
+// call site (a loop body with two or three inlined transforms is 37-43 KB of SASS and misses the 32 KB instruction
+// cache on every iteration: ncu `stall_no_instruction` 0.96 per issue in the first version) and its input is
+// staged one transform ahead with cp.async.  Algebra pinned on the CPU by scripts/fft/model.py (numpy) and
+// scripts/fft/emul.cu (thread-by-thread run of fftcore.cuh).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -30,16 +33,49 @@ namespace fftc {
 using fft::cmul;
 using fft::cmulc;
 
-// idx may be up to one period outside [0, n)
-__device__ __forceinline__ float2 load_sig(const float2* __restrict__ sig, long long idx, int n, int linear) {
-    if (idx < 0) {
-        if (linear) return make_float2(0.f, 0.f);
-        idx += n;
-    } else if (idx >= n) {
-        if (linear) return make_float2(0.f, 0.f);
-        idx -= n;
+// ---- asynchronous, thread-private input staging --------------------------------------------------------------
+// Thread t copies the 16 samples it will itself transform (elements n1 T + t) into its own shared-memory slots
+// with cp.async (8-byte copies, zero fill through src-size 0), one transform ahead; cp.async.wait_group makes its
+// own copies visible to it, so the staging needs no block-wide barrier and no branch.  The copies of the next
+// transform are issued after the first barrier of the current one (fft_n2p's hook), when the slots have been read.
+__device__ __forceinline__ void cp_async8(float2* dst, const float2* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage sig[(base + i)], i = n1 T + t < len (zero beyond; circular mod n, or zero outside [0, n) when linear);
+// base + i may be up to one period outside [0, n)
+template <int T>
+__device__ __forceinline__ void stage_sig(float2* stg, int t, const float2* __restrict__ sig, long long base, int len,
+                                          int n, int linear) {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+        const int i = n1 * T + t;
+        long long idx = base + i;
+        bool ok = i < len;
+        if (linear) {
+            ok = ok && idx >= 0 && idx < n;
+        } else {
+            idx += (idx < 0) ? n : 0;
+            idx -= (idx >= n) ? n : 0;
+        }
+        cp_async8(stg + i, sig + (ok ? idx : 0), ok);
     }
-    return __ldg(sig + idx);
+}
+
+template <int T>
+__device__ __forceinline__ void fetch_staged(float2 (&v)[16], const float2* stg, int t) {
+    cp_async_wait_all();
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = stg[n1 * T + t];
 }
 
 // exp(-2 pi i f len / L) for register r of thread t (exact argument reduction in integers)
@@ -66,14 +102,17 @@ struct LsCorrParams {
     const float2* tw;
 };
 
+// shared memory: [fft::Smem (2 exchange buffers, twiddles) | staging L float2]
+template <int R3> constexpr int lscorr_smem_float2() { return fft::Geo<R3>::SMEM_FLOAT2 + fft::Geo<R3>::L; }
+
+// The CTA walks the items (block b, channel w), w = 0: reference, w = 1: surveillance.
 template <int R3>
 __global__ void __launch_bounds__(16 * R3) lscorr_fft_kernel(const __grid_constant__ LsCorrParams p) {
     using G = fft::Geo<R3>;
     extern __shared__ __align__(16) float2 sm[];
     const int t = threadIdx.x;
     const fft::Smem<R3> S(sm);
-    fft::stage_twiddles<R3>(sm, p.tw, t);
-    __syncthreads();
+    float2* stg = sm + G::SMEM_FLOAT2;
     const float2* ref = p.ref + (size_t)blockIdx.y * p.frame_stride;
     const float2* srv = p.srv + (size_t)blockIdx.y * p.frame_stride;
     const int b0 = blockIdx.x * p.bpc;
@@ -81,64 +120,75 @@ __global__ void __launch_bounds__(16 * R3) lscorr_fft_kernel(const __grid_consta
     // a previous block of exactly L/2 samples: e_b = (-1)^f = (-1)^k1, one sign per thread
     const float sgn = ((t / R3) & 1) ? -1.f : 1.f;
 
-    float2 accC[16], accX[16], Xp[16], Xn[16], v[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) accC[r] = accX[r] = Xp[r] = make_float2(0.f, 0.f);
-    int prev_len = 0;
-    for (int b = b0; b <= b1; ++b) {                       // b == b1: look-ahead only (cross terms of block b1 - 1)
-        const bool owned = b < b1;
+    // block b: where it starts and how long it is; b == nb is what follows the channel (circular: block 0;
+    // linear: zeros, and the `peek` samples of srv that slide in)
+    auto block_geo = [&](int b, long long& start, int& ln) {
+        if (b < p.nb) { start = (long long)b * p.Bu; ln = (b == p.nb - 1) ? p.last : p.Bu; }
+        else if (p.linear) { start = p.n; ln = p.Bu; }
+        else { start = 0; ln = p.Bu; }
+    };
+    auto issue = [&](int it) {
         long long start;
         int ln;
-        if (b < p.nb) { start = (long long)b * p.Bu; ln = (b == p.nb - 1) ? p.last : p.Bu; }
-        else if (p.linear) { start = p.n; ln = p.Bu; }     // what follows the channel: zeros (and the peek samples of srv)
-        else { start = 0; ln = p.Bu; }                     // circular: block 0 follows the last block
-        // ---- reference block
+        block_geo(b0 + (it >> 1), start, ln);
+        if (it & 1) stage_sig<G::T>(stg, t, srv, start - p.peek, ln, p.n, p.linear);
+        else stage_sig<G::T>(stg, t, ref, start, ln, p.n, p.linear);
+        cp_async_commit();
+    };
+
+    const int nitems = 2 * (b1 - b0 + 1);           // block b1 is look-ahead only (cross terms of block b1 - 1)
+    issue(0);
+    fft::stage_twiddles<R3>(sm, p.tw, t);
+    __syncthreads();
+
+    float2 accC[16], accX[16], Xp[16], Q[16], v[16];
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const int i = n1 * G::T + t;
-            Xn[n1] = (i < ln) ? load_sig(ref, start + i, p.n, p.linear) : make_float2(0.f, 0.f);
-        }
-        // surveillance block (shifted by -peek): issue the loads before the first transform
+    for (int r = 0; r < 16; ++r) accC[r] = accX[r] = Xp[r] = Q[r] = make_float2(0.f, 0.f);
+    int prev_len = 0;
+#pragma unroll 1
+    for (int it = 0; it < nitems; ++it) {
+        fetch_staged<G::T>(v, stg, t);
+        fft::fft_n2p<R3>(v, t, S, [&] { if (it + 1 < nitems) issue(it + 1); });
+        const int b = b0 + (it >> 1);
+        if ((it & 1) == 0) {
+            // Q = Xp conj(e) [previous block's cross term] + Xn [own term];  accC += Q conj(Xn)
+            const bool owned = b < b1, has_prev = b > b0;
+            const bool half = (prev_len * 2 == G::L);
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const int i = n1 * G::T + t;
-            v[n1] = (i < ln) ? load_sig(srv, start + i - p.peek, p.n, p.linear) : make_float2(0.f, 0.f);
-        }
-        fft::fft_n2p<R3>(Xn, t, S);
-        fft::fft_n2p<R3>(v, t, S);
-        const bool has_prev = b > b0;
-        const bool half = (prev_len * 2 == G::L);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            // Q = Xp conj(e) [prev block's cross term] + Xn [own term];  accC += Q conj(Xn), accX += Q conj(S)
-            float2 q = make_float2(0.f, 0.f);
-            if (has_prev) {
-                if (half) q = make_float2(sgn * Xp[r].x, sgn * Xp[r].y);
-                else q = cmulc(Xp[r], shift_tw<R3>(t, r, prev_len));
+            for (int r = 0; r < 16; ++r) {
+                float2 q = make_float2(0.f, 0.f);
+                if (has_prev) {
+                    if (half) q = make_float2(sgn * Xp[r].x, sgn * Xp[r].y);
+                    else q = cmulc(Xp[r], shift_tw<R3>(t, r, prev_len));
+                }
+                if (owned) { q.x += v[r].x; q.y += v[r].y; }
+                const float2 zc = cmulc(q, v[r]);
+                accC[r].x += zc.x; accC[r].y += zc.y;
+                Q[r] = q;
+                Xp[r] = v[r];
             }
-            if (owned) { q.x += Xn[r].x; q.y += Xn[r].y; }
-            const float2 zc = cmulc(q, Xn[r]);
-            const float2 zx = cmulc(q, v[r]);
-            accC[r].x += zc.x; accC[r].y += zc.y;
-            accX[r].x += zx.x; accX[r].y += zx.y;
-            Xp[r] = Xn[r];
+            long long start;
+            block_geo(b, start, prev_len);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {                  // accX += Q conj(S)
+                const float2 zx = cmulc(Q[r], v[r]);
+                accX[r].x += zx.x; accX[r].y += zx.y;
+            }
         }
-        prev_len = ln;
     }
     const float inv = 1.0f / (float)G::L;
-    float2* row = p.partial + ((size_t)(blockIdx.y * 2 + 0) * gridDim.x + blockIdx.x) * p.HT;
-    fft::fft_p2n<R3>(accC, t, S);
+#pragma unroll 1
+    for (int w = 0; w < 2; ++w) {
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int m = n1 * G::T + t;
-        if (m < p.M) row[m] = make_float2(accC[n1].x * inv, accC[n1].y * inv);
-    }
-    row += (size_t)gridDim.x * p.HT;
-    fft::fft_p2n<R3>(accX, t, S);
+        for (int r = 0; r < 16; ++r) v[r] = w ? accX[r] : accC[r];
+        fft::fft_p2n<R3>(v, t, S);
+        float2* row = p.partial + ((size_t)(blockIdx.y * 2 + w) * gridDim.x + blockIdx.x) * p.HT;
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int m = n1 * G::T + t;
-        if (m < p.M) row[m] = make_float2(accX[n1].x * inv, accX[n1].y * inv);
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int m = n1 * G::T + t;
+            if (m < p.M) row[m] = make_float2(v[n1].x * inv, v[n1].y * inv);
+        }
     }
 }
 
@@ -183,41 +233,52 @@ struct FirFftParams {
     const float2* tw;
 };
 
+template <int R3> constexpr int fir_smem_float2() { return fft::Geo<R3>::SMEM_FLOAT2 + fft::Geo<R3>::L; }
+
 template <int R3>
 __global__ void __launch_bounds__(16 * R3) fir_fft_kernel(const __grid_constant__ FirFftParams p) {
     using G = fft::Geo<R3>;
     extern __shared__ __align__(16) float2 sm[];
     const int t = threadIdx.x;
     const fft::Smem<R3> S(sm);
-    fft::stage_twiddles<R3>(sm, p.tw, t);
-    __syncthreads();
+    float2* stg = sm + G::SMEM_FLOAT2;
     const float2* ref = p.ref + (size_t)blockIdx.y * p.frame_stride;
     const float2* srv = p.srv + (size_t)blockIdx.y * p.frame_stride;
     float2* out = p.out + (size_t)blockIdx.y * p.frame_stride;
     const float2* wp = p.wp + (size_t)blockIdx.y * G::L;
     const int Bf = G::L - p.M + 1;
     const float inv = 1.0f / (float)G::L;
+    auto issue = [&](int sgm) {
+        stage_sig<G::T>(stg, t, ref, (long long)sgm * Bf + p.peek - (p.M - 1), G::L, p.n, p.linear);
+        cp_async_commit();
+    };
+    if ((int)blockIdx.x < p.nseg) issue(blockIdx.x);
+    fft::stage_twiddles<R3>(sm, p.tw, t);
+    __syncthreads();
+#pragma unroll 1
     for (int sgm = blockIdx.x; sgm < p.nseg; sgm += gridDim.x) {
         const long long p0 = (long long)sgm * Bf;
         float2 v[16];
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1)
-            v[n1] = load_sig(ref, p0 + p.peek - (p.M - 1) + n1 * G::T + t, p.n, p.linear);
-        fft::fft_n2p<R3>(v, t, S);
+        fetch_staged<G::T>(v, stg, t);
+        fft::fft_n2p<R3>(v, t, S, [&] { if (sgm + (int)gridDim.x < p.nseg) issue(sgm + gridDim.x); });
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const float2 y = cmul(v[r], __ldg(wp + r * G::T + t));
             v[r] = make_float2(y.x, -y.y);                   // transform of conj(Y) = L conj(y)
+        }
+        float2 sv[16];                                       // surveillance samples of this segment: in flight during the transform
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int i = n1 * G::T + t;
+            const long long o = p0 + i;
+            sv[n1] = (i < Bf && o < p.n) ? __ldg(srv + o) : make_float2(0.f, 0.f);
         }
         fft::fft_p2n<R3>(v, t, S);
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
             const int i = n1 * G::T + t;
             const long long o = p0 + i;
-            if (i < Bf && o < p.n) {
-                const float2 s = __ldg(srv + o);
-                out[o] = make_float2(s.x - v[n1].x * inv, s.y + v[n1].y * inv);
-            }
+            if (i < Bf && o < p.n) out[o] = make_float2(sv[n1].x - v[n1].x * inv, sv[n1].y + v[n1].y * inv);
         }
     }
 }
@@ -238,87 +299,98 @@ struct CafFftParams {
     const float2* tw;
 };
 
+// shared memory: [fft::Smem | staging L float2 | window staging L float]
+template <int R3> constexpr int caf_smem_float2() { return fft::Geo<R3>::SMEM_FLOAT2 + fft::Geo<R3>::L + fft::Geo<R3>::L / 2; }
+
+// Items of a Doppler block: per segment the surveillance samples (kind 0), with FUSED the reference samples the
+// clutter filter needs (kind 1), and the windowed reference (kind 2); one transform call site for all of them.
 template <int R3, bool FUSED>
 __global__ void __launch_bounds__(16 * R3) caf_fft_kernel(const __grid_constant__ CafFftParams p) {
     using G = fft::Geo<R3>;
+    constexpr int NK = FUSED ? 3 : 2;
     extern __shared__ __align__(16) float2 sm[];
     const int t = threadIdx.x;
     const fft::Smem<R3> S(sm);
-    fft::stage_twiddles<R3>(sm, p.tw, t);
-    __syncthreads();
+    float2* stg = sm + G::SMEM_FLOAT2;
+    float* wst = reinterpret_cast<float*>(stg + G::L);
     const float2* ref = p.ref + (size_t)blockIdx.y * p.frame_stride;
     const float2* srv = p.srv + (size_t)blockIdx.y * p.frame_stride;
     const float2* wp = FUSED ? p.wp + (size_t)blockIdx.y * G::L : nullptr;
     const float inv = 1.0f / (float)G::L;
+    bool tw_staged = false;
+#pragma unroll 1
     for (int j = blockIdx.x; j < p.F; j += gridDim.x) {
         long long lo = (long long)j * p.D + p.c0 - (p.ntaps - 1);
         long long hi = (long long)j * p.D + p.c0 + 1;
         if (lo < 0) lo = 0;
         if (hi > p.n) hi = p.n;
-        float2 acc[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
-        if (hi > lo) {
-            const int len = (int)(hi - lo);
-            const int nseg = (len + p.Bmax - 1) / p.Bmax;
-            const int Bs = (len + nseg - 1) / nseg;
-            for (int q = 0; q < nseg; ++q) {
-                const long long i0 = lo + (long long)q * Bs;
-                const int ln = (int)min((long long)Bs, hi - i0);
-                float2 sg[16], v[16];
-                // surveillance segment: L samples from i0 (circular); positions >= ln + R are never used by lags 0..R
-#pragma unroll
-                for (int n1 = 0; n1 < 16; ++n1) {
-                    long long idx = i0 + n1 * G::T + t;
-                    if (idx >= p.n) idx -= p.n;
-                    if (idx >= p.n) idx %= p.n;              // n < L only for tiny inputs
-                    sg[n1] = __ldg(srv + idx);
-                }
-                if (FUSED) {
+        const int len = hi > lo ? (int)(hi - lo) : 0;
+        const int nseg = (len + p.Bmax - 1) / p.Bmax;
+        const int Bs = nseg ? (len + nseg - 1) / nseg : 0;
+        const int nitems = nseg * NK;
+        auto issue = [&](int it) {
+            const int q = it / NK, kind = FUSED ? it - q * NK : 2 * (it - q * NK);
+            const long long i0 = lo + (long long)q * Bs;
+            const int ln = (int)min((long long)Bs, hi - i0);
+            if (kind == 0) {
+                // L samples from i0 (circular); positions >= ln + R are never reached by lags 0..R
+                stage_sig<G::T>(stg, t, srv, i0, G::L, p.n, 0);
+            } else if (kind == 1) {
+                stage_sig<G::T>(stg, t, ref, i0 + p.peek - (p.M - 1), G::L, p.n, 0);
+            } else {
+                stage_sig<G::T>(stg, t, ref, i0, ln, p.n, 0);
+                if (p.win) {
 #pragma unroll
                     for (int n1 = 0; n1 < 16; ++n1) {
-                        long long idx = i0 + p.peek - (p.M - 1) + n1 * G::T + t;
-                        if (idx < 0) idx += p.n;
-                        if (idx >= p.n) idx -= p.n;
-                        if (idx < 0 || idx >= p.n) idx = ((idx % p.n) + p.n) % p.n;
-                        v[n1] = __ldg(ref + idx);
+                        const int i = n1 * G::T + t;
+                        cp_async4(wst + i, p.win + (i < ln ? i0 + i : 0), i < ln);
                     }
                 }
-                fft::fft_n2p<R3>(sg, t, S);
-                if (FUSED) {
-                    fft::fft_n2p<R3>(v, t, S);
+            }
+            cp_async_commit();
+        };
+        if (nitems) issue(0);
+        if (!tw_staged) {
+            fft::stage_twiddles<R3>(sm, p.tw, t);
+            __syncthreads();
+            tw_staged = true;
+        }
+        float2 acc[16], sg[16], v[16];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const float2 y = cmul(v[r], __ldg(wp + r * G::T + t));
-                        sg[r].x -= y.x;
-                        sg[r].y -= y.y;
-                    }
-                }
-                // x segment: ref * window, zero padded
+        for (int r = 0; r < 16; ++r) acc[r] = sg[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int it = 0; it < nitems; ++it) {
+            const int q = it / NK, kind = FUSED ? it - q * NK : 2 * (it - q * NK);
+            fetch_staged<G::T>(v, stg, t);
+            if (kind == 2 && p.win) {
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) {
-                    const int i = n1 * G::T + t;
-                    float2 x = make_float2(0.f, 0.f);
-                    if (i < ln) {
-                        x = __ldg(ref + i0 + i);
-                        if (p.win) {
-                            const float w = __ldg(p.win + i0 + i);
-                            x.x *= w;
-                            x.y *= w;
-                        }
-                    }
-                    v[n1] = x;
+                    const float w = wst[n1 * G::T + t];
+                    v[n1].x *= w;
+                    v[n1].y *= w;
                 }
-                fft::fft_n2p<R3>(v, t, S);
+            }
+            fft::fft_n2p<R3>(v, t, S, [&] { if (it + 1 < nitems) issue(it + 1); });
+            if (kind == 0) {
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
+                for (int r = 0; r < 16; ++r) sg[r] = v[r];
+            } else if (kind == 1) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {               // cleaned surveillance spectrum: S - R_seg W'
+                    const float2 y = cmul(v[r], __ldg(wp + r * G::T + t));
+                    sg[r].x -= y.x;
+                    sg[r].y -= y.y;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {               // acc += X conj(S_clean)
                     const float2 z = cmulc(v[r], sg[r]);
                     acc[r].x += z.x;
                     acc[r].y += z.y;
                 }
             }
-            fft::fft_p2n<R3>(acc, t, S);
         }
+        if (nitems) fft::fft_p2n<R3>(acc, t, S);
         float2* row = p.P + ((size_t)blockIdx.y * p.F + j) * p.HT;
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {

@@ -23,14 +23,32 @@ struct NlmsParams {
     int peek;
     float mu;
     int block_len;
+    // a batch of independent frames, one CTA each (gridDim.x): frame f reads ref/srv + f * frame_stride, writes
+    // out + f * frame_stride; init / taps_out advance by filter_len + peek taps per frame (init_shared: every frame
+    // starts from the same init taps)
+    long long frame_stride;
+    int init_shared;
 };
+
+__device__ __forceinline__ NlmsParams nlms_frame_params(const NlmsParams& g) {
+    NlmsParams p = g;
+    const size_t f = blockIdx.x;
+    const int M = g.filter_len + g.peek;
+    p.ref += f * g.frame_stride;
+    p.srv += f * g.frame_stride;
+    p.out += f * g.frame_stride;
+    if (p.init && !g.init_shared) p.init += f * M;
+    if (p.taps_out) p.taps_out += f * M;
+    return p;
+}
 
 constexpr int NLMS_TILE = 1024;      // samples staged per shared-memory tile
 constexpr int NLMS_MAXT = 4;         // max taps per thread (M <= 4096)
 
 template <int KT>
-__global__ void __launch_bounds__(1024) nlms_kernel(const __grid_constant__ NlmsParams p) {
+__global__ void __launch_bounds__(1024) nlms_kernel(const __grid_constant__ NlmsParams pg) {
     extern __shared__ __align__(16) float2 nsm[];
+    const NlmsParams p = nlms_frame_params(pg);
     const int M = p.filter_len + p.peek;
     const int nsteps = p.n - M;
     const int tid = threadIdx.x;

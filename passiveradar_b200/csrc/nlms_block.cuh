@@ -32,8 +32,9 @@ constexpr int NB_PAD = 64;           // extra reference samples staged behind a 
 //   Gs    [NB_L][NB_L + 1]           g(m, m + delta)
 //   es    [NB_L]                     mu conj(e_l) / p_l ;  invp [NB_L] floats (mu / p_m)
 template <int KT>
-__global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_constant__ NlmsParams p) {
+__global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_constant__ NlmsParams pg) {
     extern __shared__ __align__(16) float2 nbs[];
+    const NlmsParams p = nlms_frame_params(pg);
     const int M = p.filter_len + p.peek;
     const int Mpad = (M + 1) & ~1;
     const int nsteps = p.n - M;

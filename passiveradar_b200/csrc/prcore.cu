@@ -174,9 +174,29 @@ std::atomic<int> g_fft{1};            // FFT-domain correlation / overlap-save k
 std::atomic<int> g_fft_min_n{8192};   // ... for channels of at least this many samples (PRC_FFT_MIN_N)
 std::once_flag g_env_once;
 
+// Workspaces of a thread that called with stream == NULL.  They are released when the thread exits (dask's thread pool
+// retires worker threads): otherwise every short-lived caller would strand ~60 MB of device memory until prc_shutdown.
 struct TlsCtx {
     Ctx* ctx[64] = {nullptr};
     uint64_t epoch = 0;
+    ~TlsCtx() {
+        if (epoch != g_epoch.load()) return;              // prc_shutdown already freed them
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (epoch != g_epoch.load()) return;
+        for (Ctx*& c : ctx) {
+            if (!c) continue;
+            for (size_t i = 0; i < g_all_ctx.size(); ++i)
+                if (g_all_ctx[i] == c) {
+                    g_all_ctx.erase(g_all_ctx.begin() + i);
+                    break;
+                }
+            if (c->stream) cudaStreamSynchronize(c->stream);
+            for (ProfRec& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+            c->release();
+            delete c;
+            c = nullptr;
+        }
+    }
 };
 thread_local TlsCtx g_tls;
 
@@ -1338,8 +1358,9 @@ int direct_xambg_device(Ctx* c, const float2* ref, const float2* srv, long long 
     return PRC_OK;
 }
 
+// bt.nf independent frames run as one CTA each (the recurrence of a frame is serial, the frames are not)
 int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek, float mu,
-                int block_len, const float2* init, float2* out, float2* taps_out) {
+                int block_len, const float2* init, float2* out, float2* taps_out, Batch bt = Batch{}, bool init_shared = true) {
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
     if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
         return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
@@ -1349,6 +1370,7 @@ int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int f
     NlmsParams p{};
     p.ref = ref; p.srv = srv; p.init = init; p.out = out; p.taps_out = taps_out;
     p.n = (int)n; p.filter_len = filter_len; p.peek = peek; p.mu = mu; p.block_len = block_len;
+    p.frame_stride = bt.nf > 1 ? bt.stride : 0; p.init_shared = init_shared ? 1 : 0;
     const int kt = M <= 1024 ? 1 : (M <= 2048 ? 2 : 4);
     const int threads = std::min(1024, ((ceil_div(M, kt) + 31) / 32) * 32);
     const size_t sm = (size_t)(NLMS_TILE + ((M + 1) & ~1) + NLMS_TILE) * sizeof(float2) + 64 * sizeof(float4);
@@ -1357,14 +1379,14 @@ int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int f
         // exact evaluation 32 samples at a time (nlms_block.cuh), 4x the speed of the sample-serial kernel at
         // config 4; block_len > 1 (block_NLMS) freezes the taps inside a user block
         const size_t sb = nlms_block_smem(M);
-        if (kt == 1) nlms_block_kernel<1><<<1, NB_THREADS, sb, c->stream>>>(p);
-        else if (kt == 2) nlms_block_kernel<2><<<1, NB_THREADS, sb, c->stream>>>(p);
-        else nlms_block_kernel<4><<<1, NB_THREADS, sb, c->stream>>>(p);
+        if (kt == 1) nlms_block_kernel<1><<<bt.nf, NB_THREADS, sb, c->stream>>>(p);
+        else if (kt == 2) nlms_block_kernel<2><<<bt.nf, NB_THREADS, sb, c->stream>>>(p);
+        else nlms_block_kernel<4><<<bt.nf, NB_THREADS, sb, c->stream>>>(p);
         return check_launch("nlms_block_kernel");
     }
-    if (kt == 1) nlms_kernel<1><<<1, threads, sm, c->stream>>>(p);
-    else if (kt == 2) nlms_kernel<2><<<1, threads, sm, c->stream>>>(p);
-    else nlms_kernel<4><<<1, threads, sm, c->stream>>>(p);
+    if (kt == 1) nlms_kernel<1><<<bt.nf, threads, sm, c->stream>>>(p);
+    else if (kt == 2) nlms_kernel<2><<<bt.nf, threads, sm, c->stream>>>(p);
+    else nlms_kernel<4><<<bt.nf, threads, sm, c->stream>>>(p);
     return check_launch("nlms_kernel");
 }
 
@@ -1676,6 +1698,106 @@ int prc_nlms_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_l
         CU(cudaMemcpyAsync(out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
         if (taps_out) CU(cudaMemcpyAsync(taps_out, c->nl_taps.p, mb, cudaMemcpyDeviceToHost, c->stream));
     }
+    return finish(c, flags);
+}
+
+int prc_nlms_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                        int filter_len, int peek, float mu, int block_len, const prc_c64* init_taps, prc_c64* out,
+                        prc_c64* taps_out, int mem_kind, int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (nframes < 1) return fail(PRC_E_INVALID, "nframes=%d invalid", nframes);
+    if (nframes > 1 && frame_stride < n) return fail(PRC_E_INVALID, "frame_stride=%lld smaller than n=%lld", (long long)frame_stride, (long long)n);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const int M = filter_len + peek;
+    const size_t mb = (size_t)(M > 0 ? M : 1) * sizeof(float2);
+    Batch bt;
+    bt.nf = nframes;
+    bt.stride = nframes > 1 ? frame_stride : n;
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    const float2* dinit = reinterpret_cast<const float2*>(init_taps);
+    float2* dout = reinterpret_cast<float2*>(out);
+    float2* dtaps = reinterpret_cast<float2*>(taps_out);
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->ref.ensure(nb * nframes));
+        TRY(c->srv.ensure(nb * nframes));
+        TRY(c->clean.ensure(nb * nframes));
+        TRY(c->nl_taps.ensure(mb * nframes));
+        for (int fr = 0; fr < nframes; ++fr) {
+            CU(cudaMemcpyAsync(c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (init_taps) {
+            TRY(c->nl_init.ensure(mb));
+            CU(cudaMemcpyAsync(c->nl_init.p, init_taps, mb, cudaMemcpyHostToDevice, c->stream));
+            dinit = c->nl_init.as<float2>();
+        }
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dout = c->clean.as<float2>();
+        dtaps = c->nl_taps.as<float2>();
+        bt.stride = n;
+    }
+    TRY(nlms_device(c, dref, dsrv, n, filter_len, peek, mu, block_len, dinit, dout, dtaps, bt, true));
+    if (mem_kind == PRC_MEM_HOST) {
+        const size_t fs = (size_t)(nframes > 1 ? frame_stride : n);
+        for (int fr = 0; fr < nframes; ++fr)
+            CU(cudaMemcpyAsync(out + fr * fs, c->clean.as<float2>() + (size_t)fr * n, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (taps_out) CU(cudaMemcpyAsync(taps_out, c->nl_taps.p, mb * nframes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return finish(c, flags);
+}
+
+int prc_xambg_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                         int range_bins, int freq_bins, const void* window, prc_c64* out, int mem_kind, int device,
+                         void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (bad_mem_kind(mem_kind)) return fail(PRC_E_INVALID, "mem_kind=%d invalid", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (nframes < 1) return fail(PRC_E_INVALID, "nframes=%d invalid", nframes);
+    if (nframes > 1 && frame_stride < n) return fail(PRC_E_INVALID, "frame_stride=%lld smaller than n=%lld", (long long)frame_stride, (long long)n);
+    if (freq_bins < 1 || range_bins < 0) return fail(PRC_E_INVALID, "freq_bins=%d / range_bins=%d invalid", freq_bins, range_bins);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t nb = (size_t)n * sizeof(float2);
+    const size_t ob = (size_t)freq_bins * (range_bins + 1) * sizeof(float2);
+    Batch bt;
+    bt.nf = nframes;
+    bt.stride = nframes > 1 ? frame_stride : n;
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* dsrv = reinterpret_cast<const float2*>(srv);
+    float2* dout = reinterpret_cast<float2*>(out);
+    if (mem_kind == PRC_MEM_HOST) {
+        TRY(c->ref.ensure(nb * nframes));
+        TRY(c->srv.ensure(nb * nframes));
+        TRY(c->out.ensure(ob * nframes));
+        for (int fr = 0; fr < nframes; ++fr) {
+            CU(cudaMemcpyAsync(c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+        }
+        dref = c->ref.as<float2>();
+        dsrv = c->srv.as<float2>();
+        dout = c->out.as<float2>();
+        bt.stride = n;
+    }
+    const float* win32;
+    TRY(stage_window(c, window, n, mem_kind, flags, &win32));
+    const long long D = n / freq_bins;
+    const bool batched = D >= 2 && caf_fft_plan(n, range_bins, freq_bins, D + 1, D, true, 0).on;
+    if (batched || nframes == 1) {
+        TRY(xambg_device(c, dref, dsrv, n, range_bins, freq_bins, win32, nullptr, 0, dout, false, false, bt));
+    } else {
+        for (int fr = 0; fr < nframes; ++fr)       // direct-form kernels, frame by frame
+            TRY(xambg_device(c, dref + (size_t)fr * bt.stride, dsrv + (size_t)fr * bt.stride, n, range_bins, freq_bins, win32,
+                             nullptr, 0, dout + (size_t)fr * freq_bins * (range_bins + 1)));
+    }
+    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, c->out.p, ob * nframes, cudaMemcpyDeviceToHost, c->stream));
     return finish(c, flags);
 }
 

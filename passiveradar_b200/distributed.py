@@ -111,3 +111,87 @@ def process_stream(process_local, ref_frames, srv_frames, nframes, n, src=0, dev
     if not gather:
         return maps_l, idx
     return gather_maps(maps_l, nframes, src, mode, group), idx
+
+
+def stream_benchmark(pipe, ref_d, srv_d, maps_d, nframes_total, chunk, rank, world, device, src=0):
+    """BASELINE config 3 with real staging: a stream of ``nframes_total`` CPI frames is held by the ingest rank ``src``
+    (its resident frames stand in for the stream), frame ``f`` belongs to rank ``f % world``; the ingest rank sends every
+    other rank its (ref, srv) frames in chunks of ``chunk`` frames over NCCL point-to-point (NVLink / NVSwitch) on a side
+    stream, double buffered against the rank's compute of the previous chunk; results stay on the rank.  This is the
+    traffic the dask graph's halo staging (main.py:178-181) turns into when the chunks live on different GPUs.
+    Returns (rank 0) a dict: whole-job frames/s including the staging, bytes the ingest rank sent, its egress GB/s.
+    Time = max over ranks of the device time between the first enqueue and the last result."""
+    import torch
+    import torch.distributed as dist
+    n = ref_d.shape[1]
+    res = ref_d.shape[0]
+    per_rank = nframes_total // world
+    nchunks = -(-per_rank // chunk)
+    side = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+    bufs = None
+    if rank != src:
+        bufs = [(torch.empty((chunk, n), dtype=torch.complex64, device=device), torch.empty((chunk, n), dtype=torch.complex64, device=device))
+                for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]       # staging of buffer k complete
+    freed = [torch.cuda.Event() for _ in range(2)]       # compute on buffer k complete
+
+    def run_once():
+        for c in range(nchunks + 1):
+            m = min(chunk, per_rank - c * chunk) if c < nchunks else 0
+            # ---- staging of chunk c (side stream)
+            if c < nchunks:
+                with torch.cuda.stream(side):
+                    if rank == src:
+                        ops = []
+                        for r in range(world):
+                            if r == src:
+                                continue
+                            o = ((c * world + r) * chunk) % max(1, res - chunk + 1)
+                            ops.append(dist.P2POp(dist.isend, _as_real(ref_d[o:o + m]), r))
+                            ops.append(dist.P2POp(dist.isend, _as_real(srv_d[o:o + m]), r))
+                        for w in dist.batch_isend_irecv(ops):
+                            w.wait()
+                    else:
+                        k = c & 1
+                        if c >= 2:
+                            side.wait_event(freed[k])
+                        rb, sb = bufs[k]
+                        ops = [dist.P2POp(dist.irecv, _as_real(rb[:m]), src), dist.P2POp(dist.irecv, _as_real(sb[:m]), src)]
+                        for w in dist.batch_isend_irecv(ops):
+                            w.wait()
+                        ready[k].record(side)
+            # ---- compute of chunk c - 1 (main stream)
+            if c >= 1:
+                cc = c - 1
+                mm = min(chunk, per_rank - cc * chunk)
+                o = (cc * chunk) % max(1, res - chunk + 1)
+                if rank == src:
+                    pipe.run_device(ref_d[o:o + mm], srv_d[o:o + mm], maps_d[o:o + mm])
+                else:
+                    k = cc & 1
+                    main.wait_event(ready[k])
+                    rb, sb = bufs[k]
+                    pipe.run_device(rb[:mm], sb[:mm], maps_d[o:o + mm])
+                    freed[k].record(main)
+        main.wait_stream(side)
+
+    run_once()                                           # warm-up (NCCL channels, workspaces)
+    torch.cuda.synchronize(device)
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    run_once()
+    e1.record(main)
+    torch.cuda.synchronize(device)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank != 0:
+        return None
+    sent = (world - 1) * per_rank * 2 * n * 8
+    return {"frames": per_rank * world, "value": per_rank * world / (ms * 1e-3), "unit": "frames/s", "ms": round(ms, 3),
+            "chunk_frames": chunk, "ingest_rank_sent_bytes": sent, "ingest_egress_GBps": round(sent / (ms * 1e-3) / 1e9, 1),
+            "staging": "NCCL point-to-point (batch_isend_irecv) from rank 0 on a side stream, double buffered against compute",
+            "note": "frame f -> rank f % world; rank 0 holds the stream in HBM and also computes its own share; the limiter is "
+                    "rank 0's NVLink egress when ingest_egress_GBps approaches the ~770 GB/s peer-copy figure"}
