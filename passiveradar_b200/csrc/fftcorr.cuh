@@ -52,22 +52,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // stage sig[(base + i)], i = n1 T + t < len (zero beyond; circular mod n, or zero outside [0, n) when linear);
-// base + i may be up to one period outside [0, n)
+// base may be up to one period outside [0, n) and the L elements cross the end of the channel at most once.
+// A copy that is switched off (src-size 0) reads nothing, so its source address is not sanitised.
 template <int T>
 __device__ __forceinline__ void stage_sig(float2* stg, int t, const float2* __restrict__ sig, long long base, int len,
                                           int n, int linear) {
+    int lo = 0, hi = len, wrap = 0x7fffffff;
+    if (linear) {                                   // valid i: 0 <= base + i < n
+        lo = base < 0 ? (int)(-base) : 0;
+        const long long h = (long long)n - base;
+        hi = h < (long long)len ? (h < 0 ? 0 : (int)h) : len;
+    } else {
+        if (base < 0) base += n;
+        if (base >= n) base -= n;
+        wrap = (int)(n - base);                     // first element that has wrapped around
+    }
+    const float2* p0 = sig + base;
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
         const int i = n1 * T + t;
-        long long idx = base + i;
-        bool ok = i < len;
-        if (linear) {
-            ok = ok && idx >= 0 && idx < n;
-        } else {
-            idx += (idx < 0) ? n : 0;
-            idx -= (idx >= n) ? n : 0;
-        }
-        cp_async8(stg + i, sig + (ok ? idx : 0), ok);
+        const int off = i - (i >= wrap ? n : 0);
+        cp_async8(stg + i, p0 + off, i >= lo && i < hi);
     }
 }
 

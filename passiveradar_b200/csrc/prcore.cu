@@ -589,7 +589,7 @@ int ls_fft_corr(Ctx* c, const LsFftPlan& pl, const float2* ref, const float2* sr
     p.partial = c->partial.as<float2>(); p.HT = pl.HT; p.tw = tw;
     {
         ProfScope ps(c, K_LAGCORR_LS);
-        PRC_R3_SWITCH(pl.r3, (fftc::lscorr_fft_kernel<R3><<<dim3(pl.ncta, bt.nf), 16 * R3, fft_smem(R3), c->stream>>>(p)));
+        PRC_R3_SWITCH(pl.r3, (fftc::lscorr_fft_kernel<R3><<<dim3(pl.ncta, bt.nf), 16 * R3, fftc::lscorr_smem_float2<R3>() * sizeof(float2), c->stream>>>(p)));
     }
     return check_launch("lscorr_fft_kernel");
 }
@@ -605,7 +605,10 @@ int levinson_launch(Ctx* c, int nchunk, int HT, int M, double reg, int nf) {
     lp.status = c->status.as<int>();
     {
         ProfScope ps(c, K_LEVINSON);
-        if (M <= 1024) levinson_kernel<1><<<nf, 1024, levinson_smem(M, 1024), c->stream>>>(lp);
+        // one thread per unknown (a CTA of 1024 threads would own a whole SM's registers and could not share it
+        // with the other slots' transform CTAs; the recursion only ever uses ceil(M / 32) warps)
+        const int thr = std::max(64, (M + 31) & ~31);
+        if (M <= 1024) levinson_kernel<1><<<nf, thr, levinson_smem(M, thr), c->stream>>>(lp);
         else levinson_kernel<4><<<nf, 512, levinson_smem(M, 512), c->stream>>>(lp);
     }
     return check_launch("levinson_kernel");
@@ -641,7 +644,7 @@ int fir_fft(Ctx* c, int r3, const float2* ref, const float2* srv, float2* out, l
     const int per_frame = std::max(1, std::min(p.nseg, ceil_div(4 * c->nsm, bt.nf)));
     {
         ProfScope ps(c, K_FIR);
-        PRC_R3_SWITCH(r3, (fftc::fir_fft_kernel<R3><<<dim3(per_frame, bt.nf), 16 * R3, fft_smem(R3), c->stream>>>(p)));
+        PRC_R3_SWITCH(r3, (fftc::fir_fft_kernel<R3><<<dim3(per_frame, bt.nf), 16 * R3, fftc::fir_smem_float2<R3>() * sizeof(float2), c->stream>>>(p)));
     }
     return check_launch("fir_fft_kernel");
 }
@@ -686,8 +689,8 @@ int caf_fft(Ctx* c, const CafFftPlan& pl, const float2* ref, const float2* srv, 
     const dim3 grid(F, bt.nf);
     {
         ProfScope ps(c, K_LAGCORR_CAF);
-        if (wp) { PRC_R3_SWITCH(pl.r3, (fftc::caf_fft_kernel<R3, true><<<grid, 16 * R3, fft_smem(R3), c->stream>>>(p))); }
-        else { PRC_R3_SWITCH(pl.r3, (fftc::caf_fft_kernel<R3, false><<<grid, 16 * R3, fft_smem(R3), c->stream>>>(p))); }
+        if (wp) { PRC_R3_SWITCH(pl.r3, (fftc::caf_fft_kernel<R3, true><<<grid, 16 * R3, fftc::caf_smem_float2<R3>() * sizeof(float2), c->stream>>>(p))); }
+        else { PRC_R3_SWITCH(pl.r3, (fftc::caf_fft_kernel<R3, false><<<grid, 16 * R3, fftc::caf_smem_float2<R3>() * sizeof(float2), c->stream>>>(p))); }
     }
     return check_launch("caf_fft_kernel");
 }

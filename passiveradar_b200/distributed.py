@@ -113,75 +113,118 @@ def process_stream(process_local, ref_frames, srv_frames, nframes, n, src=0, dev
     return gather_maps(maps_l, nframes, src, mode, group), idx
 
 
-def stream_benchmark(pipe, ref_d, srv_d, maps_d, nframes_total, chunk, rank, world, device, src=0):
-    """BASELINE config 3 with real staging: a stream of ``nframes_total`` CPI frames is held by the ingest rank ``src``
-    (its resident frames stand in for the stream), frame ``f`` belongs to rank ``f % world``; the ingest rank sends every
-    other rank its (ref, srv) frames in chunks of ``chunk`` frames over NCCL point-to-point (NVLink / NVSwitch) on a side
-    stream, double buffered against the rank's compute of the previous chunk; results stay on the rank.  This is the
-    traffic the dask graph's halo staging (main.py:178-181) turns into when the chunks live on different GPUs.
-    Returns (rank 0) a dict: whole-job frames/s including the staging, bytes the ingest rank sent, its egress GB/s.
-    Time = max over ranks of the device time between the first enqueue and the last result."""
+def stream_frames(source, process, nframes_total, chunk, n, rank, world, device, src=0):
+    """Config-3 staging: a stream of ``nframes_total`` CPI frames is held by the ingest rank ``src``; frame ``f`` belongs
+    to rank ``f % world``.  The ingest rank sends every other rank its (ref, srv) frames in chunks of ``chunk`` frames
+    with point-to-point operations (NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests); on CUDA devices the
+    transfers run on a side stream into two alternating buffers while the main stream computes the previous chunk.
+
+    ``source(ids) -> (ref, srv)``   ingest rank only: tensors ``(len(ids), n)`` complex64 on ``device`` for global frame ids
+    ``process(ref, srv, first)``    every rank: consume a chunk whose first LOCAL frame index is ``first`` (enqueue only)
+
+    This is the traffic the dask graph's chunk staging (main.py:169-194, overlap at :178-181) turns into when the
+    chunks live on different GPUs.  Returns the number of local frames processed."""
     import torch
     import torch.distributed as dist
-    n = ref_d.shape[1]
-    res = ref_d.shape[0]
-    per_rank = nframes_total // world
-    nchunks = -(-per_rank // chunk)
-    side = torch.cuda.Stream(device=device)
-    main = torch.cuda.current_stream(device)
+    cuda = torch.device(device).type == "cuda"
+    per_rank = len(shard_indices(nframes_total, rank, world))
+    counts = [len(shard_indices(nframes_total, r, world)) for r in range(world)]
+    nchunks = -(-max(counts) // chunk) if counts else 0
+    side = torch.cuda.Stream(device=device) if cuda else None
+    main = torch.cuda.current_stream(device) if cuda else None
     bufs = None
     if rank != src:
         bufs = [(torch.empty((chunk, n), dtype=torch.complex64, device=device), torch.empty((chunk, n), dtype=torch.complex64, device=device))
                 for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]       # staging of buffer k complete
-    freed = [torch.cuda.Event() for _ in range(2)]       # compute on buffer k complete
+    ready = [torch.cuda.Event() for _ in range(2)] if cuda else None      # staging of buffer k complete
+    freed = [torch.cuda.Event() for _ in range(2)] if cuda else None      # compute on buffer k complete
 
-    def run_once():
-        for c in range(nchunks + 1):
-            m = min(chunk, per_rank - c * chunk) if c < nchunks else 0
-            # ---- staging of chunk c (side stream)
-            if c < nchunks:
+    def ids_of(r, c):
+        lo, hi = c * chunk, min((c + 1) * chunk, counts[r])
+        return [k * world + r for k in range(lo, hi)]
+
+    def stage(c):
+        if rank == src:
+            ops, keep = [], []
+            for r in range(world):
+                ids = ids_of(r, c)
+                if r == src or not ids:
+                    continue
+                rr, ss = source(ids)
+                keep.append((rr, ss))
+                ops.append(dist.P2POp(dist.isend, _as_real(rr), r))
+                ops.append(dist.P2POp(dist.isend, _as_real(ss), r))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        else:
+            m = len(ids_of(rank, c))
+            if m:
+                k = c & 1
+                if cuda and c >= 2:
+                    side.wait_event(freed[k])
+                rb, sb = bufs[k]
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, _as_real(rb[:m]), src),
+                                                 dist.P2POp(dist.irecv, _as_real(sb[:m]), src)]):
+                    w.wait()
+                if cuda:
+                    ready[k].record(side)
+
+    def compute(c):
+        ids = ids_of(rank, c)
+        if not ids:
+            return
+        if rank == src:
+            rr, ss = source(ids)
+            process(rr, ss, c * chunk)
+        else:
+            k = c & 1
+            if cuda:
+                main.wait_event(ready[k])
+            rb, sb = bufs[k]
+            process(rb[:len(ids)], sb[:len(ids)], c * chunk)
+            if cuda:
+                freed[k].record(main)
+
+    for c in range(nchunks + 1):
+        if c < nchunks:
+            if cuda:
                 with torch.cuda.stream(side):
-                    if rank == src:
-                        ops = []
-                        for r in range(world):
-                            if r == src:
-                                continue
-                            o = ((c * world + r) * chunk) % max(1, res - chunk + 1)
-                            ops.append(dist.P2POp(dist.isend, _as_real(ref_d[o:o + m]), r))
-                            ops.append(dist.P2POp(dist.isend, _as_real(srv_d[o:o + m]), r))
-                        for w in dist.batch_isend_irecv(ops):
-                            w.wait()
-                    else:
-                        k = c & 1
-                        if c >= 2:
-                            side.wait_event(freed[k])
-                        rb, sb = bufs[k]
-                        ops = [dist.P2POp(dist.irecv, _as_real(rb[:m]), src), dist.P2POp(dist.irecv, _as_real(sb[:m]), src)]
-                        for w in dist.batch_isend_irecv(ops):
-                            w.wait()
-                        ready[k].record(side)
-            # ---- compute of chunk c - 1 (main stream)
-            if c >= 1:
-                cc = c - 1
-                mm = min(chunk, per_rank - cc * chunk)
-                o = (cc * chunk) % max(1, res - chunk + 1)
-                if rank == src:
-                    pipe.run_device(ref_d[o:o + mm], srv_d[o:o + mm], maps_d[o:o + mm])
-                else:
-                    k = cc & 1
-                    main.wait_event(ready[k])
-                    rb, sb = bufs[k]
-                    pipe.run_device(rb[:mm], sb[:mm], maps_d[o:o + mm])
-                    freed[k].record(main)
+                    stage(c)
+            else:
+                stage(c)
+        if c >= 1:
+            compute(c - 1)
+    if cuda:
         main.wait_stream(side)
+    return per_rank
 
-    run_once()                                           # warm-up (NCCL channels, workspaces)
+
+def stream_benchmark(pipe, ref_d, srv_d, maps_d, nframes_total, chunk, rank, world, device, src=0):
+    """Time :func:`stream_frames` with the rank's FramePipeline: the ingest rank's resident frames stand in for the
+    stream (frame f reads resident frame f mod resident).  Returns (rank 0) whole-job frames/s INCLUDING the staging, the
+    bytes the ingest rank sent and its egress bandwidth; time = max over ranks of the device time of one pass."""
+    import torch
+    import torch.distributed as dist
+    n = ref_d.shape[1]
+    res = ref_d.shape[0]
+    nmaps = maps_d.shape[0]
+
+    def source(ids):
+        o = ids[0] % max(1, res - len(ids) + 1)          # a contiguous run of distinct resident frames (no gather copy)
+        return ref_d[o:o + len(ids)], srv_d[o:o + len(ids)]
+
+    def process(rr, ss, first):
+        o = first % max(1, nmaps - rr.shape[0] + 1)
+        pipe.run_device(rr, ss, maps_d[o:o + rr.shape[0]])
+
+    main = torch.cuda.current_stream(device)
+    stream_frames(source, process, nframes_total, chunk, n, rank, world, device, src)       # warm-up (NCCL channels)
     torch.cuda.synchronize(device)
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
-    run_once()
+    local = stream_frames(source, process, nframes_total, chunk, n, rank, world, device, src)
     e1.record(main)
     torch.cuda.synchronize(device)
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
@@ -189,9 +232,9 @@ def stream_benchmark(pipe, ref_d, srv_d, maps_d, nframes_total, chunk, rank, wor
     ms = float(t.item())
     if rank != 0:
         return None
-    sent = (world - 1) * per_rank * 2 * n * 8
-    return {"frames": per_rank * world, "value": per_rank * world / (ms * 1e-3), "unit": "frames/s", "ms": round(ms, 3),
+    sent = (nframes_total - local) * 2 * n * 8
+    return {"frames": nframes_total, "value": nframes_total / (ms * 1e-3), "unit": "frames/s", "ms": round(ms, 3),
             "chunk_frames": chunk, "ingest_rank_sent_bytes": sent, "ingest_egress_GBps": round(sent / (ms * 1e-3) / 1e9, 1),
-            "staging": "NCCL point-to-point (batch_isend_irecv) from rank 0 on a side stream, double buffered against compute",
+            "staging": "NCCL point-to-point (batch_isend_irecv) from rank 0 on a side stream, two alternating buffers per rank",
             "note": "frame f -> rank f % world; rank 0 holds the stream in HBM and also computes its own share; the limiter is "
                     "rank 0's NVLink egress when ingest_egress_GBps approaches the ~770 GB/s peer-copy figure"}

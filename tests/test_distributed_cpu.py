@@ -77,3 +77,49 @@ def test_scatter_process_gather_world2_gloo(mode):
     assert results["rank1"][0]
     assert results["rank1"][1][0] == D.shard_indices(nframes, 1, 2, mode).tolist()
     assert results["rank1"][1][1]
+
+
+def _stream_worker(rank, world, port, nframes, n, chunk, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11)
+        ref = torch.view_as_complex(torch.randn(nframes, n, 2, generator=g))      # every rank can rebuild the stream to check
+        srv = torch.view_as_complex(torch.randn(nframes, n, 2, generator=g))
+        got = []
+
+        def source(ids):
+            assert rank == 0
+            return ref[ids].contiguous(), srv[ids].contiguous()
+
+        def process(rr, ss, first):
+            got.append((first, rr.clone(), ss.clone()))
+
+        cnt = D.stream_frames(source, process, nframes, chunk, n, rank, world, torch.device("cpu"), src=0)
+        ids = D.shard_indices(nframes, rank, world)
+        ok = cnt == len(ids) and sum(g_[1].shape[0] for g_ in got) == len(ids)
+        for first, rr, ss in got:
+            want = ids[first:first + rr.shape[0]]
+            ok = ok and torch.equal(rr, ref[want]) and torch.equal(ss, srv[want])
+        q.put((rank, bool(ok), [g_[0] for g_ in got]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nframes,chunk", [(11, 2), (8, 4), (3, 5)])
+def test_stream_frames_world2_gloo(nframes, chunk):
+    """Config-3 staging plumbing: the ingest rank hands every rank its frames f % world chunk by chunk, in order."""
+    world, n = 2, 16
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, nframes, n, chunk, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    for rank, ok, firsts in res:
+        assert ok, (rank, firsts)
+        assert firsts == sorted(firsts)

@@ -204,3 +204,66 @@ def test_short_lived_threads_do_not_strand_device_memory():
     torch.cuda.synchronize()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 64 * 2 ** 20, (free0, free1)       # 24 stranded workspaces would be > 100 MB
+
+
+# ------------------------------------------------------------------ config-3 staging over NCCL (needs >= 2 GPUs)
+def _nccl_stream_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from passiveradar_b200 import distributed as D
+    from passiveradar_b200.frames import FramePipeline
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        n, F, R, nframes, chunk = 2 ** 16, 32, 40, 13, 3
+        frames = [synth.make_frame(n, "P1", frame=70 + i) for i in range(nframes)]       # every rank can rebuild the stream
+        pipe = FramePipeline(n, R, F, filter_len=40, device=rank, batch=chunk, nslots=2)
+        ids = D.shard_indices(nframes, rank, world)
+        maps = torch.zeros((len(ids), F, R + 1), dtype=torch.complex64, device=dev)
+        ref_all = srv_all = None
+        if rank == 0:
+            ref_all = torch.from_numpy(np.stack([f[0] for f in frames])).to(dev)
+            srv_all = torch.from_numpy(np.stack([f[1] for f in frames])).to(dev)
+
+        def source(gids):
+            idx = torch.as_tensor(gids, device=dev)
+            return ref_all.index_select(0, idx), srv_all.index_select(0, idx)
+
+        def process(rr, ss, first):
+            pipe.run_device(rr, ss, maps[first:first + rr.shape[0]])
+
+        cnt = D.stream_frames(source, process, nframes, chunk, n, rank, world, dev, src=0)
+        torch.cuda.synchronize(dev)
+        worst = 0.0
+        for k, f in enumerate(ids):
+            ref, srv = frames[f]
+            want = prb.fast_xambg(ref, prb.LS_Filter(ref, srv, 40, device=rank), R, F, n, signal.get_window(("kaiser", 5.0), n), device=rank)
+            worst = max(worst, G.rel_inf(maps[k].cpu().numpy()[:, :, None], want))
+        q.put((rank, cnt == len(ids), worst))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stream_frames_over_nccl_world2():
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_stream_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, worst in res:
+        assert ok and worst <= 2e-6, (rank, ok, worst)
