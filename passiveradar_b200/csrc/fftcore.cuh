@@ -47,8 +47,15 @@ template <int R3> struct Geo {
     static constexpr int SMEM_FLOAT2 = 2 * EX + TW1 + TW2;
 };
 
+// complex add / subtract: on the device one packed FP32x2 instruction each (FADD2 / FFMA2 with -1: the same two
+// roundings as the scalar form, half the issue slots -- the transforms are issue-bound, not FP32-lane-bound)
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(PRC_SCALAR_FFT)
+PRC_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+PRC_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+#else
 PRC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 PRC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 PRC_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 PRC_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a conj(b)
 PRC_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }      // a * (-i)

@@ -3,11 +3,12 @@
 //
 //   lscorr_fft_kernel   c[m] = sum_i ref[i] conj(ref[i+m]),  x[m] = sum_i ref[i] conj(srv[i+m-peek]),  m < M
 //                       (first column of A^H A and A^H srv of LS_Filter, reference clutter_removal.py:34-45, up to the
-//                       conjugation levinson_kernel applies).  The channel is cut into nb zero-padded blocks of
-//                       Bu <= L/2 samples; with X_b, S_b their length-L spectra the sum over blocks of
-//                       X_b conj(X_b + e_b X_{b+1}) (e_b = shift by the block length) is the spectrum of the lag
-//                       sums for 0 <= m < M <= L/2 -- two transforms per block, spectra accumulated in registers,
-//                       one permuted->natural transform per correlation and CTA at the end.
+//                       conjugation levinson_kernel applies).  The channel is cut into segments of Bs <= L - M + 1
+//                       samples; per segment X = spectrum of the zero-padded reference segment, Yr / Ys = spectra of
+//                       the L reference / surveillance samples that start with it: X conj(Yr) and X conj(Ys) are the
+//                       spectra of the segment's lag sums for 0 <= m < M (lags reach at most L - 1, no wrap).
+//                       Three transforms per segment, spectra accumulated in registers over the CTA's segments, one
+//                       permuted->natural transform per correlation and CTA at the end.
 //   taps_spectrum_kernel  W'(f): spectrum of the solved taps placed at (k - (M-1)) mod L, in permuted order.
 //   fir_fft_kernel      out = srv - circular FIR(ref, w)  (clutter_removal.py:51) by overlap-save: one forward
 //                       transform of L reference samples, times W', one transform back, L - M + 1 outputs.
@@ -53,7 +54,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // stage sig[(base + i)], i = n1 T + t < len (zero beyond; circular mod n, or zero outside [0, n) when linear);
 // base may be up to one period outside [0, n) and the L elements cross the end of the channel at most once.
-// A copy that is switched off (src-size 0) reads nothing, so its source address is not sanitised.
+// A copy that is switched off (src-size 0) reads nothing, so its source address is not sanitised.  Rows n1 that lie
+// entirely beyond len are neither copied nor fetched (zero-padded operands: a third to a half of the staging traffic).
 template <int T>
 __device__ __forceinline__ void stage_sig(float2* stg, int t, const float2* __restrict__ sig, long long base, int len,
                                           int n, int linear) {
@@ -68,30 +70,24 @@ __device__ __forceinline__ void stage_sig(float2* stg, int t, const float2* __re
         wrap = (int)(n - base);                     // first element that has wrapped around
     }
     const float2* p0 = sig + base;
+    const int rows = (len + T - 1) / T;
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-        const int i = n1 * T + t;
-        const int off = i - (i >= wrap ? n : 0);
-        cp_async8(stg + i, p0 + off, i >= lo && i < hi);
+        if (n1 < rows) {
+            const int i = n1 * T + t;
+            const int off = i - (i >= wrap ? n : 0);
+            cp_async8(stg + i, p0 + off, i >= lo && i < hi);
+        }
     }
 }
 
+// len: the same length the item was staged with
 template <int T>
-__device__ __forceinline__ void fetch_staged(float2 (&v)[16], const float2* stg, int t) {
+__device__ __forceinline__ void fetch_staged(float2 (&v)[16], const float2* stg, int t, int len) {
     cp_async_wait_all();
+    const int rows = (len + T - 1) / T;
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) v[n1] = stg[n1 * T + t];
-}
-
-// exp(-2 pi i f len / L) for register r of thread t (exact argument reduction in integers)
-template <int R3>
-__device__ __forceinline__ float2 shift_tw(int t, int r, int len) {
-    constexpr int L = fft::Geo<R3>::L;
-    const int f = fft::perm_freq<R3>(t, r);
-    const int q = (int)(((long long)f * len) & (L - 1));
-    float s, c;
-    sincospif(-2.0f * (float)q / (float)L, &s, &c);
-    return make_float2(c, s);
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = (n1 < rows) ? stg[n1 * T + t] : make_float2(0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------ LS correlations
@@ -100,8 +96,7 @@ struct LsCorrParams {
     const float2* srv;
     long long frame_stride;
     int n, M, peek, linear;
-    int nb, Bu, last;          // nb blocks of Bu samples, the last one `last` samples
-    int bpc;                   // blocks per CTA
+    int nseg, Bs;              // nseg segments of Bs samples (the last one shorter), Bs <= L - M + 1
     float2* partial;           // [frame][2][gridDim.x][HT]
     int HT;
     const float2* tw;
@@ -110,7 +105,8 @@ struct LsCorrParams {
 // shared memory: [fft::Smem (2 exchange buffers, twiddles) | staging L float2]
 template <int R3> constexpr int lscorr_smem_float2() { return fft::Geo<R3>::SMEM_FLOAT2 + fft::Geo<R3>::L; }
 
-// The CTA walks the items (block b, channel w), w = 0: reference, w = 1: surveillance.
+// CTA c of a frame takes segments c, c + gridDim.x, ...; items per segment: 0 = zero-padded reference segment (X),
+// 1 = L reference samples from the segment start (Yr), 2 = L surveillance samples from start - peek (Ys).
 template <int R3>
 __global__ void __launch_bounds__(16 * R3) lscorr_fft_kernel(const __grid_constant__ LsCorrParams p) {
     using G = fft::Geo<R3>;
@@ -120,65 +116,50 @@ __global__ void __launch_bounds__(16 * R3) lscorr_fft_kernel(const __grid_consta
     float2* stg = sm + G::SMEM_FLOAT2;
     const float2* ref = p.ref + (size_t)blockIdx.y * p.frame_stride;
     const float2* srv = p.srv + (size_t)blockIdx.y * p.frame_stride;
-    const int b0 = blockIdx.x * p.bpc;
-    const int b1 = min(b0 + p.bpc, p.nb);
-    // a previous block of exactly L/2 samples: e_b = (-1)^f = (-1)^k1, one sign per thread
-    const float sgn = ((t / R3) & 1) ? -1.f : 1.f;
+    const int nmine = ((int)blockIdx.x < p.nseg) ? (p.nseg - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nitems = 3 * nmine;
 
-    // block b: where it starts and how long it is; b == nb is what follows the channel (circular: block 0;
-    // linear: zeros, and the `peek` samples of srv that slide in)
-    auto block_geo = [&](int b, long long& start, int& ln) {
-        if (b < p.nb) { start = (long long)b * p.Bu; ln = (b == p.nb - 1) ? p.last : p.Bu; }
-        else if (p.linear) { start = p.n; ln = p.Bu; }
-        else { start = 0; ln = p.Bu; }
+    auto item_len = [&](int it) {
+        const int q = it / 3, kind = it - 3 * q;
+        const int sgm = blockIdx.x + q * gridDim.x;
+        return kind == 0 ? min(p.Bs, p.n - sgm * p.Bs) : G::L;
     };
     auto issue = [&](int it) {
-        long long start;
-        int ln;
-        block_geo(b0 + (it >> 1), start, ln);
-        if (it & 1) stage_sig<G::T>(stg, t, srv, start - p.peek, ln, p.n, p.linear);
-        else stage_sig<G::T>(stg, t, ref, start, ln, p.n, p.linear);
+        const int q = it / 3, kind = it - 3 * q;
+        const int sgm = blockIdx.x + q * gridDim.x;
+        const long long i0 = (long long)sgm * p.Bs;
+        if (kind == 0) stage_sig<G::T>(stg, t, ref, i0, min(p.Bs, p.n - sgm * p.Bs), p.n, p.linear);
+        else if (kind == 1) stage_sig<G::T>(stg, t, ref, i0, G::L, p.n, p.linear);
+        else stage_sig<G::T>(stg, t, srv, i0 - p.peek, G::L, p.n, p.linear);
         cp_async_commit();
     };
 
-    const int nitems = 2 * (b1 - b0 + 1);           // block b1 is look-ahead only (cross terms of block b1 - 1)
-    issue(0);
+    if (nitems) issue(0);
     fft::stage_twiddles<R3>(sm, p.tw, t);
     __syncthreads();
 
-    float2 accC[16], accX[16], Xp[16], Q[16], v[16];
+    float2 accC[16], accX[16], X[16], v[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) accC[r] = accX[r] = Xp[r] = Q[r] = make_float2(0.f, 0.f);
-    int prev_len = 0;
+    for (int r = 0; r < 16; ++r) accC[r] = accX[r] = X[r] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int it = 0; it < nitems; ++it) {
-        fetch_staged<G::T>(v, stg, t);
+        const int kind = it % 3;
+        fetch_staged<G::T>(v, stg, t, item_len(it));
         fft::fft_n2p<R3>(v, t, S, [&] { if (it + 1 < nitems) issue(it + 1); });
-        const int b = b0 + (it >> 1);
-        if ((it & 1) == 0) {
-            // Q = Xp conj(e) [previous block's cross term] + Xn [own term];  accC += Q conj(Xn)
-            const bool owned = b < b1, has_prev = b > b0;
-            const bool half = (prev_len * 2 == G::L);
+        if (kind == 0) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                float2 q = make_float2(0.f, 0.f);
-                if (has_prev) {
-                    if (half) q = make_float2(sgn * Xp[r].x, sgn * Xp[r].y);
-                    else q = cmulc(Xp[r], shift_tw<R3>(t, r, prev_len));
-                }
-                if (owned) { q.x += v[r].x; q.y += v[r].y; }
-                const float2 zc = cmulc(q, v[r]);
-                accC[r].x += zc.x; accC[r].y += zc.y;
-                Q[r] = q;
-                Xp[r] = v[r];
+            for (int r = 0; r < 16; ++r) X[r] = v[r];
+        } else if (kind == 1) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {                  // accC += X conj(Yr)
+                const float2 z = cmulc(X[r], v[r]);
+                accC[r].x += z.x; accC[r].y += z.y;
             }
-            long long start;
-            block_geo(b, start, prev_len);
         } else {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {                  // accX += Q conj(S)
-                const float2 zx = cmulc(Q[r], v[r]);
-                accX[r].x += zx.x; accX[r].y += zx.y;
+            for (int r = 0; r < 16; ++r) {                  // accX += X conj(Ys)
+                const float2 z = cmulc(X[r], v[r]);
+                accX[r].x += z.x; accX[r].y += z.y;
             }
         }
     }
@@ -264,7 +245,7 @@ __global__ void __launch_bounds__(16 * R3) fir_fft_kernel(const __grid_constant_
     for (int sgm = blockIdx.x; sgm < p.nseg; sgm += gridDim.x) {
         const long long p0 = (long long)sgm * Bf;
         float2 v[16];
-        fetch_staged<G::T>(v, stg, t);
+        fetch_staged<G::T>(v, stg, t, G::L);
         fft::fft_n2p<R3>(v, t, S, [&] { if (sgm + (int)gridDim.x < p.nseg) issue(sgm + gridDim.x); });
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -345,10 +326,11 @@ __global__ void __launch_bounds__(16 * R3) caf_fft_kernel(const __grid_constant_
             } else {
                 stage_sig<G::T>(stg, t, ref, i0, ln, p.n, 0);
                 if (p.win) {
+                    const int rows = (ln + G::T - 1) / G::T;
 #pragma unroll
                     for (int n1 = 0; n1 < 16; ++n1) {
                         const int i = n1 * G::T + t;
-                        cp_async4(wst + i, p.win + (i < ln ? i0 + i : 0), i < ln);
+                        if (n1 < rows) cp_async4(wst + i, p.win + i0 + i, i < ln);
                     }
                 }
             }
@@ -366,13 +348,16 @@ __global__ void __launch_bounds__(16 * R3) caf_fft_kernel(const __grid_constant_
 #pragma unroll 1
         for (int it = 0; it < nitems; ++it) {
             const int q = it / NK, kind = FUSED ? it - q * NK : 2 * (it - q * NK);
-            fetch_staged<G::T>(v, stg, t);
+            fetch_staged<G::T>(v, stg, t, kind == 2 ? (int)min((long long)Bs, hi - (lo + (long long)q * Bs)) : G::L);
             if (kind == 2 && p.win) {
+                const int rows = ((int)min((long long)Bs, hi - (lo + (long long)q * Bs)) + G::T - 1) / G::T;
 #pragma unroll
                 for (int n1 = 0; n1 < 16; ++n1) {
-                    const float w = wst[n1 * G::T + t];
-                    v[n1].x *= w;
-                    v[n1].y *= w;
+                    if (n1 < rows) {
+                        const float w = wst[n1 * G::T + t];
+                        v[n1].x *= w;
+                        v[n1].y *= w;
+                    }
                 }
             }
             fft::fft_n2p<R3>(v, t, S, [&] { if (it + 1 < nitems) issue(it + 1); });

@@ -543,35 +543,26 @@ int fft_twiddles(Ctx* c, int r3, const float2** tw) {
     return PRC_OK;
 }
 
-// ---- LS correlations: block partition of the channel
+// ---- LS correlations: segments of the channel
 struct LsFftPlan {
     bool on = false;
-    int r3 = 8, nb = 0, Bu = 0, last = 0, bpc = 0, ncta = 0, HT = 0;
+    int r3 = 8, nseg = 0, Bs = 0, ncta = 0, HT = 0;
 };
 
 LsFftPlan ls_fft_plan(const Ctx* c, long long n, int M, int nf) {
     LsFftPlan pl;
     if (!g_fft.load() || n < g_fft_min_n.load() || M < 1 || M > 2048) return pl;
     pl.r3 = M <= 1024 ? 8 : 16;
-    const int L = 256 * pl.r3, B = L / 2;
+    const int L = 256 * pl.r3;
     if (n < 2 * L) return pl;
-    const long long nb0 = (n + B - 1) / B;
-    bool found = false;
-    for (long long nb = std::max<long long>(nb0, 2); nb <= nb0 + 8 && !found; ++nb) {
-        const long long Bu = (n + nb - 1) / nb;
-        const long long last = n - (nb - 1) * Bu;
-        // every block must be followed by at least M - 1 samples of the next one, and lags < M must not alias
-        if (last >= std::max(M - 1, 1) && Bu >= M - 1 && Bu <= B && M <= L - Bu + 1) {
-            pl.nb = (int)nb; pl.Bu = (int)Bu; pl.last = (int)last;
-            found = true;
-        }
-    }
-    if (!found) return pl;
-    // CTAs of one transform group (16 R3 threads); ~3 resident per SM over the whole batch, >= 4 blocks each so
-    // that the look-ahead block and the two final transforms stay a small share
-    const long long want = std::max<long long>(1, (3ll * c->nsm + nf - 1) / nf);
-    pl.bpc = (int)std::max<long long>(4, (pl.nb + want - 1) / want);
-    pl.ncta = ceil_div(pl.nb, pl.bpc);
+    const int bmax = L - M + 1;                        // lags 0..M-1 of a segment stay inside its L-sample window
+    pl.nseg = (int)((n + bmax - 1) / bmax);
+    pl.Bs = (int)((n + pl.nseg - 1) / pl.nseg);
+    pl.nseg = (int)((n + pl.Bs - 1) / pl.Bs);
+    // CTAs of one transform group (16 R3 threads), 3 resident per SM: the whole batch is ONE wave of CTAs, every CTA
+    // walks its share of a frame's segments (any split works: segments are independent)
+    const long long slots = 3ll * c->nsm;
+    pl.ncta = (int)std::max<long long>(1, std::min<long long>(pl.nseg, slots / nf));
     pl.HT = (M + 1) & ~1;
     pl.on = true;
     return pl;
@@ -585,7 +576,7 @@ int ls_fft_corr(Ctx* c, const LsFftPlan& pl, const float2* ref, const float2* sr
     fftc::LsCorrParams p{};
     p.ref = ref; p.srv = srv; p.frame_stride = bt.stride;
     p.n = (int)n; p.M = M; p.peek = peek; p.linear = linear ? 1 : 0;
-    p.nb = pl.nb; p.Bu = pl.Bu; p.last = pl.last; p.bpc = pl.bpc;
+    p.nseg = pl.nseg; p.Bs = pl.Bs;
     p.partial = c->partial.as<float2>(); p.HT = pl.HT; p.tw = tw;
     {
         ProfScope ps(c, K_LAGCORR_LS);

@@ -21,51 +21,34 @@ def direct_lags(x, s, lags, n, linear=False):
     return out
 
 
-def ls_partition(n, M, L):
-    """blocks of equal length Bu (last one shorter), nb of them; None if not eligible"""
-    B = L // 2
-    nb0 = -(-n // B)
-    for nb in range(max(nb0, 2), nb0 + 9):
-        Bu = -(-n // nb)
-        last = n - (nb - 1) * Bu
-        if Bu <= B and last >= max(M - 1, 1) and M <= L - Bu + 1:
-            return nb, Bu, last
-    return None
-
-
 def model_lscorr(ref, srv, M, peek, L, linear=False):
+    """segments of Bs <= L - M + 1 samples; X = zero-padded reference segment, Yr / Ys = the L reference / surveillance
+    samples that start with it (surveillance shifted by -peek); sum over segments of X conj(Y) is the spectrum of the lag sums"""
     n = len(ref)
-    nb, Bu, last = ls_partition(n, M, L)
-    f = np.arange(L)
+    bmax = L - M + 1
+    nseg = -(-n // bmax)
+    Bs = -(-n // nseg)
+    nseg = -(-n // Bs)
 
-    def blk(sig, b, off):
-        """zero-padded block b of sig shifted by off: sig[(b*Bu + i + off)], i < len_b; block nb = what follows the
-        last block (linear mode: zeros except for the `off` samples that slide in)"""
-        ln = Bu if b != nb - 1 else last
-        idx = (b * Bu if b < nb else n) + np.arange(ln) + off
+    def take(sig, base, ln):
+        idx = base + np.arange(L)
         if linear:
             v = np.where((idx >= 0) & (idx < n), sig[np.clip(idx, 0, n - 1)], 0)
         else:
             v = sig[idx % n]
-        z = np.zeros(L, complex)
-        z[:ln] = v
-        return np.fft.fft(z), ln
+        v = v.astype(complex)
+        v[ln:] = 0
+        return np.fft.fft(v)
 
     accC = np.zeros(L, complex)
     accX = np.zeros(L, complex)
-    X = [blk(ref, b, 0) for b in range(nb + 1)]
-    S = [blk(srv, b, -peek) for b in range(nb + 1)]
-    for b in range(nb):
-        Xb, ln = X[b]
-        nxt = (b + 1) if (linear or b + 1 < nb) else 0
-        tw = np.exp(-2j * np.pi * f * ln / L)
-        Yc = Xb + tw * X[nxt][0]
-        Ys = S[b][0] + tw * S[nxt][0]
-        accC += Xb * np.conj(Yc)       # Zc = X conj(Y)
-        accX += Xb * np.conj(Ys)
-    C = np.fft.fft(accC)[:M] / L        # forward transform of Zc = L * C
-    Xc = np.fft.fft(accX)[:M] / L
-    return C, Xc
+    for q in range(nseg):
+        i0 = q * Bs
+        ln = min(Bs, n - i0)
+        X = take(ref, i0, ln)
+        accC += X * np.conj(take(ref, i0, L))
+        accX += X * np.conj(take(srv, i0 - peek, L))
+    return np.fft.fft(accC)[:M] / L, np.fft.fft(accX)[:M] / L
 
 
 def taps_spectrum(w, L):

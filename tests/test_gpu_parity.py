@@ -326,10 +326,15 @@ def test_frame_pipeline_matches_reference_golden(name, both_paths):
     assert G.rel_inf(maps[0], t_map) <= TOL
     assert G.rel_inf(maps[0], g["out"]) <= TOL + 1.2 * e_ref
     assert np.array_equal(maps[0], maps[2])                   # deterministic, slot-independent
-    # second frame (clutter + target): against the separate operators
+    # second frame (clutter + target): against the separate operators.  The direct-form path computes the same cleaned
+    # channel either way; the FFT path cleans the surveillance SPECTRUM inside the CAF kernel, a different float32
+    # evaluation of a map that is what is left after ~55 dB of cancellation: the two agree to ~1e-4 of that residual
+    # map (the reference's own complex64 map is 5e-3 from the float64 truth there)
     cleaned = prb.LS_Filter(ref2, srv2, R)
     want = prb.fast_xambg(ref2, cleaned, R, F, n, w)
-    assert G.rel_inf(maps[1], want) <= 2e-6
+    e2 = G.rel_inf(maps[1], want)
+    record_parity(f"frame_pipeline_p1_vs_separate/{name}/{both_paths}", E=e2)
+    assert e2 <= (5e-4 if both_paths == "fft" else 2e-6)
 
 
 def test_frame_pipeline_without_window_and_odd_shape(both_paths):
@@ -340,7 +345,12 @@ def test_frame_pipeline_without_window_and_odd_shape(both_paths):
     got = pipe.process(ref, srv)
     cleaned = prb.LS_Filter(ref, srv, 20, 0.5, 3)
     want = prb.fast_xambg(ref, cleaned, R, F)
-    assert G.rel_inf(got, want) <= 2e-6
+    # strong clutter (P1): see test_frame_pipeline_matches_reference_golden for the FFT path's bound
+    assert G.rel_inf(got, want) <= (5e-4 if both_paths == "fft" else 2e-6)
+    ref0, srv0 = synth.make_frame(n, "P0", frame=2)
+    got0 = pipe.process(ref0, srv0)
+    want0 = prb.fast_xambg(ref0, prb.LS_Filter(ref0, srv0, 20, 0.5, 3), R, F)
+    assert G.rel_inf(got0, want0) <= 2e-6
 
 
 # ------------------------------------------------------------------ LS_Filter_Toeplitz / LS_Filter_Multiple
