@@ -195,7 +195,7 @@ def _cpu_sample_worker(job):
     """One bounded sample of a frame on the CPU: the clutter filter on n/div samples with the full tap count (its cost
     is linear in n: data matrix, Gram and solve for LS_Filter, the recurrence for NLMS_filter) and fast_xambg on the
     FULL frame with all range lags.  Returns (estimated seconds for one whole frame, filter seconds, xambg seconds)."""
-    cfg, seed_frame, div, profile, nlms_block = job
+    cfg, seed_frame, div, profile, nlms_block, lag_div = job
     import scipy.signal as signal
     from passiveradar_b200 import synth
     LS_Filter, NLMS_filter, fast_xambg, kind = _ref_modules()
@@ -211,16 +211,21 @@ def _cpu_sample_worker(job):
         NLMS_filter(ref[:ns], srv[:ns], cfg["filter_len"], cfg["mu"], cfg["peek"])
     t_f = time.perf_counter() - t0
     t0 = time.perf_counter()
-    fast_xambg(ref, srv, R, F, n, w)
+    Rs = (R + 1) // lag_div - 1                      # lag_div > 1: a subset of the range lags (every lag costs the same)
+    fast_xambg(ref, srv, Rs, F, n, w)
     t_x = time.perf_counter() - t0
-    return t_f * div + t_x, t_f, t_x
+    return t_f * div + t_x * (R + 1) / (Rs + 1), t_f, t_x
 
 
 class CpuArm:
     """Frame-parallel pool, one process per host core (1 BLAS thread each), as SURVEY 8d asks."""
 
-    def __init__(self, cfg, procs, profile, nlms_block=1):
+    def __init__(self, cfg, procs, profile, nlms_block=1, bounded=False):
+        """bounded=False: the sample of `cpu_baseline` (one round: fast_xambg on the whole frame, every lag measured).
+        bounded=True: the reference arm's step, repeated steps + warmup times, so a step is cut to a few seconds
+        (fast_xambg on 1/8 of the range lags, clutter filter on a shorter piece)."""
         import multiprocessing as mp
+        self.bounded = bounded
         self.cfg = cfg
         self.profile = profile
         self.nlms_block = nlms_block
@@ -233,6 +238,10 @@ class CpuArm:
         # n/8 keeps a worker at ~1 GB and a few seconds.  NLMS_filter is a Python loop of 8.8 us per sample: n/32.
         big = cfg["n"] >= 2 ** 19
         self.div = (8 if cfg["clutter"] == "ls" else 32) if big else 1
+        self.lag_div = 1
+        if bounded and big:
+            self.div *= 4
+            self.lag_div = 8
         try:
             mem_gb = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
         except (ValueError, OSError):
@@ -246,7 +255,7 @@ class CpuArm:
 
     def step(self):
         """One round: every worker processes one bounded sample.  Returns (frames/s, wall seconds, est s/frame)."""
-        jobs = [(self.cfg, 1000 + self.round * self.procs + i, self.div, self.profile, self.nlms_block)
+        jobs = [(self.cfg, 1000 + self.round * self.procs + i, self.div, self.profile, self.nlms_block, self.lag_div)
                 for i in range(self.procs)]
         self.round += 1
         t0 = time.perf_counter()
@@ -266,9 +275,10 @@ class CpuArm:
         src = "the reference's own functions (baseline/_ref, unmodified)" if self.kind == "reference" else "the oracle port"
         ext = (f"{flt} on n/{self.div} = {c['n'] // self.div} samples with all {c['filter_len'] + c['peek']} taps, time x{self.div} "
                f"(EXTRAPOLATED: cost linear in n)") if self.div > 1 else f"{flt} on the full frame"
-        return (f"per worker, {src}: {ext} + fast_xambg on the FULL {c['n']}-sample frame, all {c['R'] + 1} range lags "
-                f"(measured, scipy.signal.decimate's np.roots detour bypassed bit-identically); {self.procs} workers in "
-                f"parallel, 1 BLAS thread each")
+        lags = (f"all {c['R'] + 1} range lags (measured" if self.lag_div == 1 else
+                f"{(c['R'] + 1) // self.lag_div} of {c['R'] + 1} range lags, time x{(c['R'] + 1) / ((c['R'] + 1) // self.lag_div):.2f} (EXTRAPOLATED: every lag costs the same")
+        return (f"per worker, {src}: {ext} + fast_xambg on the FULL {c['n']}-sample frame, {lags}; scipy.signal.decimate's np.roots "
+                f"detour bypassed bit-identically); {self.procs} workers in parallel, 1 BLAS thread each")
 
     def close(self):
         self.pool.terminate()
@@ -278,7 +288,7 @@ class CpuArm:
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    arm = CpuArm(cfg, args.cpu_procs, args.profile, args.nlms_block)
+    arm = CpuArm(cfg, args.cpu_procs, args.profile, args.nlms_block, bounded=(args.steps + args.warmup) > 3)
     try:
         for _ in range(args.warmup):
             arm.step()
@@ -296,7 +306,7 @@ def run_reference(args, cfg, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; f64 block sums)",
         "data": "synthetic", "config": config_dict(cfg, args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": arm.kind,
-                         "sample": arm.sample_text(), "filter_extrapolated": arm.div > 1},
+                         "sample": arm.sample_text(), "filter_extrapolated": arm.div > 1, "xambg_extrapolated": arm.lag_div > 1},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -463,16 +473,19 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
 
     # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
     nb_host = ref_base.shape[0]
+    if nlms:
+        nb_host = 74                 # NLMS runs one CTA per frame: a call must carry enough frames to use the GPU
     ref_h = pinned_empty((nb_host, n))
     srv_h = pinned_empty((nb_host, n))
-    ref_h[:] = ref_base
-    srv_h[:] = srv_base
+    for i in range(nb_host):
+        ref_h[i] = ref_base[i % ref_base.shape[0]]
+        srv_h[i] = srv_base[i % srv_base.shape[0]]
     maps_h = pinned_empty((nb_host, F, R + 1, 1))
     stage = None
     if nlms:
         stage = (torch.empty((nb_host, n), dtype=torch.complex64, device=dev), torch.empty((nb_host, n), dtype=torch.complex64, device=dev),
                  torch.empty((nb_host, F, R + 1), dtype=torch.complex64, device=dev))
-    e2e_frames_per_step = max(nb_host, int(round((24 if nlms else 640) / nb_host)) * nb_host)
+    e2e_frames_per_step = max(nb_host, int(round((74 if nlms else 640) / nb_host)) * nb_host)
     passes = e2e_frames_per_step // nb_host
     for _ in range(2):
         work.run_host(ref_h, srv_h, maps_h, stage)
@@ -494,7 +507,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
         import scipy.signal as signal
         import passiveradar_b200 as prb
         w64 = signal.get_window(("kaiser", 5.0), n)
-        pairs = [(np.array(ref_base[i % nb_host]), np.array(srv_base[i % nb_host])) for i in range(8)]
+        pairs = [(np.array(ref_base[i % ref_base.shape[0]]), np.array(srv_base[i % srv_base.shape[0]])) for i in range(8)]
 
         def one(i):
             r, s = pairs[i % 8]

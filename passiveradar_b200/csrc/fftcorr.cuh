@@ -54,40 +54,52 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // stage sig[(base + i)], i = n1 T + t < len (zero beyond; circular mod n, or zero outside [0, n) when linear);
 // base may be up to one period outside [0, n) and the L elements cross the end of the channel at most once.
-// A copy that is switched off (src-size 0) reads nothing, so its source address is not sanitised.  Rows n1 that lie
-// entirely beyond len are neither copied nor fetched (zero-padded operands: a third to a half of the staging traffic).
-template <int T>
+// A copy that is switched off (src-size 0) reads nothing, so its source address is not sanitised.
+// FULL: len == L is known at compile time.  The common case -- the L elements lie inside [0, n) -- is one LDGSTS per
+// element with immediate offsets (the index arithmetic of the general case costs as many issue slots as the copies).
+template <int T, bool FULL>
 __device__ __forceinline__ void stage_sig(float2* stg, int t, const float2* __restrict__ sig, long long base, int len,
                                           int n, int linear) {
-    int lo = 0, hi = len, wrap = 0x7fffffff;
+    if (base >= 0 && base + 16 * T <= n) {
+        const float2* p0 = sig + base + t;
+        float2* d0 = stg + t;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1)
+            if (FULL || n1 * T < len) cp_async8(d0 + n1 * T, p0 + n1 * T, FULL || n1 * T + t < len);   // rows beyond len: not staged
+        return;
+    }
+    int lo = 0, hi = FULL ? 16 * T : len, wrap = 0x7fffffff;
     if (linear) {                                   // valid i: 0 <= base + i < n
         lo = base < 0 ? (int)(-base) : 0;
         const long long h = (long long)n - base;
-        hi = h < (long long)len ? (h < 0 ? 0 : (int)h) : len;
+        hi = h < (long long)hi ? (h < 0 ? 0 : (int)h) : hi;
     } else {
         if (base < 0) base += n;
         if (base >= n) base -= n;
         wrap = (int)(n - base);                     // first element that has wrapped around
     }
     const float2* p0 = sig + base;
-    const int rows = (len + T - 1) / T;
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-        if (n1 < rows) {
-            const int i = n1 * T + t;
-            const int off = i - (i >= wrap ? n : 0);
-            cp_async8(stg + i, p0 + off, i >= lo && i < hi);
-        }
+        const int i = n1 * T + t;
+        const int off = i - (i >= wrap ? n : 0);
+        if (FULL || n1 * T < len) cp_async8(stg + i, p0 + off, i >= lo && i < hi);
     }
 }
 
-// len: the same length the item was staged with
-template <int T>
+// len: what the item was staged with (rows n1 T >= len were not staged: zero)
+template <int T, bool FULL>
 __device__ __forceinline__ void fetch_staged(float2 (&v)[16], const float2* stg, int t, int len) {
     cp_async_wait_all();
-    const int rows = (len + T - 1) / T;
+    const float2* s0 = stg + t;
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) v[n1] = (n1 < rows) ? stg[n1 * T + t] : make_float2(0.f, 0.f);
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = (FULL || n1 * T < len) ? s0[n1 * T] : make_float2(0.f, 0.f);
+}
+
+// acc += a conj(b)
+__device__ __forceinline__ void cmacc(float2& acc, const float2 a, const float2 b) {
+    acc.x = fmaf(a.x, b.x, fmaf(a.y, b.y, acc.x));
+    acc.y = fmaf(a.y, b.x, fmaf(-a.x, b.y, acc.y));
 }
 
 // ------------------------------------------------------------------------------------------------ LS correlations
@@ -119,18 +131,13 @@ __global__ void __launch_bounds__(16 * R3) lscorr_fft_kernel(const __grid_consta
     const int nmine = ((int)blockIdx.x < p.nseg) ? (p.nseg - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int nitems = 3 * nmine;
 
-    auto item_len = [&](int it) {
-        const int q = it / 3, kind = it - 3 * q;
-        const int sgm = blockIdx.x + q * gridDim.x;
-        return kind == 0 ? min(p.Bs, p.n - sgm * p.Bs) : G::L;
-    };
     auto issue = [&](int it) {
         const int q = it / 3, kind = it - 3 * q;
         const int sgm = blockIdx.x + q * gridDim.x;
         const long long i0 = (long long)sgm * p.Bs;
-        if (kind == 0) stage_sig<G::T>(stg, t, ref, i0, min(p.Bs, p.n - sgm * p.Bs), p.n, p.linear);
-        else if (kind == 1) stage_sig<G::T>(stg, t, ref, i0, G::L, p.n, p.linear);
-        else stage_sig<G::T>(stg, t, srv, i0 - p.peek, G::L, p.n, p.linear);
+        if (kind == 0) stage_sig<G::T, false>(stg, t, ref, i0, min(p.Bs, p.n - sgm * p.Bs), p.n, p.linear);
+        else if (kind == 1) stage_sig<G::T, true>(stg, t, ref, i0, G::L, p.n, p.linear);
+        else stage_sig<G::T, true>(stg, t, srv, i0 - p.peek, G::L, p.n, p.linear);
         cp_async_commit();
     };
 
@@ -144,23 +151,18 @@ __global__ void __launch_bounds__(16 * R3) lscorr_fft_kernel(const __grid_consta
 #pragma unroll 1
     for (int it = 0; it < nitems; ++it) {
         const int kind = it % 3;
-        fetch_staged<G::T>(v, stg, t, item_len(it));
+        if (kind == 0) fetch_staged<G::T, false>(v, stg, t, min(p.Bs, p.n - ((int)blockIdx.x + (it / 3) * (int)gridDim.x) * p.Bs));
+        else fetch_staged<G::T, true>(v, stg, t, G::L);
         fft::fft_n2p<R3>(v, t, S, [&] { if (it + 1 < nitems) issue(it + 1); });
         if (kind == 0) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) X[r] = v[r];
         } else if (kind == 1) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {                  // accC += X conj(Yr)
-                const float2 z = cmulc(X[r], v[r]);
-                accC[r].x += z.x; accC[r].y += z.y;
-            }
+            for (int r = 0; r < 16; ++r) cmacc(accC[r], X[r], v[r]);        // accC += X conj(Yr)
         } else {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {                  // accX += X conj(Ys)
-                const float2 z = cmulc(X[r], v[r]);
-                accX[r].x += z.x; accX[r].y += z.y;
-            }
+            for (int r = 0; r < 16; ++r) cmacc(accX[r], X[r], v[r]);        // accX += X conj(Ys)
         }
     }
     const float inv = 1.0f / (float)G::L;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(16 * R3) fir_fft_kernel(const __grid_constant_
     const int Bf = G::L - p.M + 1;
     const float inv = 1.0f / (float)G::L;
     auto issue = [&](int sgm) {
-        stage_sig<G::T>(stg, t, ref, (long long)sgm * Bf + p.peek - (p.M - 1), G::L, p.n, p.linear);
+        stage_sig<G::T, true>(stg, t, ref, (long long)sgm * Bf + p.peek - (p.M - 1), G::L, p.n, p.linear);
         cp_async_commit();
     };
     if ((int)blockIdx.x < p.nseg) issue(blockIdx.x);
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(16 * R3) fir_fft_kernel(const __grid_constant_
     for (int sgm = blockIdx.x; sgm < p.nseg; sgm += gridDim.x) {
         const long long p0 = (long long)sgm * Bf;
         float2 v[16];
-        fetch_staged<G::T>(v, stg, t, G::L);
+        fetch_staged<G::T, true>(v, stg, t, G::L);
         fft::fft_n2p<R3>(v, t, S, [&] { if (sgm + (int)gridDim.x < p.nseg) issue(sgm + gridDim.x); });
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -320,18 +322,16 @@ __global__ void __launch_bounds__(16 * R3) caf_fft_kernel(const __grid_constant_
             const int ln = (int)min((long long)Bs, hi - i0);
             if (kind == 0) {
                 // L samples from i0 (circular); positions >= ln + R are never reached by lags 0..R
-                stage_sig<G::T>(stg, t, srv, i0, G::L, p.n, 0);
+                stage_sig<G::T, true>(stg, t, srv, i0, G::L, p.n, 0);
             } else if (kind == 1) {
-                stage_sig<G::T>(stg, t, ref, i0 + p.peek - (p.M - 1), G::L, p.n, 0);
+                stage_sig<G::T, true>(stg, t, ref, i0 + p.peek - (p.M - 1), G::L, p.n, 0);
             } else {
-                stage_sig<G::T>(stg, t, ref, i0, ln, p.n, 0);
+                stage_sig<G::T, false>(stg, t, ref, i0, ln, p.n, 0);
                 if (p.win) {
-                    const int rows = (ln + G::T - 1) / G::T;
+                    const float* w0 = p.win + i0 + t;
 #pragma unroll
-                    for (int n1 = 0; n1 < 16; ++n1) {
-                        const int i = n1 * G::T + t;
-                        if (n1 < rows) cp_async4(wst + i, p.win + i0 + i, i < ln);
-                    }
+                    for (int n1 = 0; n1 < 16; ++n1)
+                        if (n1 * G::T < ln) cp_async4(wst + t + n1 * G::T, w0 + n1 * G::T, n1 * G::T + t < ln);
                 }
             }
             cp_async_commit();
@@ -348,17 +348,21 @@ __global__ void __launch_bounds__(16 * R3) caf_fft_kernel(const __grid_constant_
 #pragma unroll 1
         for (int it = 0; it < nitems; ++it) {
             const int q = it / NK, kind = FUSED ? it - q * NK : 2 * (it - q * NK);
-            fetch_staged<G::T>(v, stg, t, kind == 2 ? (int)min((long long)Bs, hi - (lo + (long long)q * Bs)) : G::L);
-            if (kind == 2 && p.win) {
-                const int rows = ((int)min((long long)Bs, hi - (lo + (long long)q * Bs)) + G::T - 1) / G::T;
+            if (kind == 2) {
+                const int ln = (int)min((long long)Bs, hi - (lo + (long long)q * Bs));
+                fetch_staged<G::T, false>(v, stg, t, ln);
+                if (p.win) {
 #pragma unroll
-                for (int n1 = 0; n1 < 16; ++n1) {
-                    if (n1 < rows) {
-                        const float w = wst[n1 * G::T + t];
-                        v[n1].x *= w;
-                        v[n1].y *= w;
+                    for (int n1 = 0; n1 < 16; ++n1) {
+                        if (n1 * G::T < ln) {
+                            const float w = wst[t + n1 * G::T];
+                            v[n1].x *= w;
+                            v[n1].y *= w;
+                        }
                     }
                 }
+            } else {
+                fetch_staged<G::T, true>(v, stg, t, G::L);
             }
             fft::fft_n2p<R3>(v, t, S, [&] { if (it + 1 < nitems) issue(it + 1); });
             if (kind == 0) {
@@ -373,11 +377,7 @@ __global__ void __launch_bounds__(16 * R3) caf_fft_kernel(const __grid_constant_
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {               // acc += X conj(S_clean)
-                    const float2 z = cmulc(v[r], sg[r]);
-                    acc[r].x += z.x;
-                    acc[r].y += z.y;
-                }
+                for (int r = 0; r < 16; ++r) cmacc(acc[r], v[r], sg[r]);         // acc += X conj(S_clean)
             }
         }
         if (nitems) fft::fft_p2n<R3>(acc, t, S);

@@ -224,7 +224,7 @@ def _nccl_stream_worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         n, F, R, nframes, chunk = 2 ** 16, 32, 40, 13, 3
-        frames = [synth.make_frame(n, "P1", frame=70 + i) for i in range(nframes)]       # every rank can rebuild the stream
+        frames = [synth.make_frame(n, "P0", frame=70 + i) for i in range(nframes)]       # every rank can rebuild the stream
         pipe = FramePipeline(n, R, F, filter_len=40, device=rank, batch=chunk, nslots=2)
         ids = D.shard_indices(nframes, rank, world)
         maps = torch.zeros((len(ids), F, R + 1), dtype=torch.complex64, device=dev)
