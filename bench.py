@@ -502,7 +502,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
     # ---- the reference's own call signatures from a thread pool (main.py:169-194 under dask's threaded scheduler):
     # pageable numpy arrays in, numpy arrays out, one library workspace per calling thread
     dropin = None
-    if rank == 0 and not nlms:
+    if rank == 0 and not nlms and not quiet:
         import concurrent.futures as cf
         import scipy.signal as signal
         import passiveradar_b200 as prb
@@ -526,7 +526,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
     # ---- what the host link can carry: plain pinned-memory H2D copies of the same buffers, nothing else running
     h2d_peak = None
     try:
-        if rank == 0:
+        if rank == 0 and not quiet:
             src = torch.from_numpy(ref_h.reshape(-1).view(np.float32))
             dst = torch.empty_like(src, device=dev)
             dst.copy_(src, non_blocking=True)
@@ -679,7 +679,8 @@ def run_sweep(args, rank, world, local_rank):
             cfg = dict(n=n, F=F, R=300, filter_len=300, peek=10, reg=1.0, clutter="ls", name=f"sweep n={n} F={F} R=300")
             a = argparse.Namespace(**vars(args))
             a.resident = max(16, min(125, (2 ** 31) // (16 * n)))
-            a.frames_per_step = max(a.resident, int(40000 * 2 ** 20 / n / max(base_steps, 1) / 10))
+            a.steps = min(base_steps, 5)
+            a.frames_per_step = max(a.resident, int(8000 * 2 ** 20 / n / a.steps))      # ~0.3 s of GPU time per point
             a.no_cpu_baseline = True
             a.no_stream = True
             line = run_b200(a, cfg, rank, world, local_rank, quiet=True)
