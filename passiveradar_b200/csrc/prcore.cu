@@ -133,6 +133,9 @@ struct Ctx {
         nl_init, nl_taps;
     int tw_F = 0;
     int status_slot = 0;      // which int of `status` the direct-form Toeplitz solve reports to
+    void* pin[2] = {nullptr, nullptr};      // page-locked bounce buffers for pageable host arrays (h2d / d2h below)
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    bool pin_ready = false;
     DBuf fft_tw[3], wp_fir, wp_caf, fftP;     // FFT-domain path: twiddle tables (L = 1024 / 2048 / 4096), taps spectra, CAF block sums
     bool fft_tw_ready[3] = {false, false, false};
     std::vector<ProfRec> recs;
@@ -150,6 +153,10 @@ struct Ctx {
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
             b->release();
+        if (pin_ready) {
+            for (int k = 0; k < 2; ++k) { cudaFreeHost(pin[k]); cudaEventDestroy(pin_ev[k]); pin[k] = nullptr; pin_ev[k] = nullptr; }
+            pin_ready = false;
+        }
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -1384,6 +1391,72 @@ int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int f
     return check_launch("nlms_kernel");
 }
 
+// ---- host <-> device copies of caller arrays.  dask hands the operators ordinary (pageable) numpy arrays from several
+// threads at once (main.py:169-194); cudaMemcpyAsync from pageable memory goes through the driver's own staging, one
+// copy at a time for the whole process.  Each workspace therefore owns two page-locked bounce buffers: the calling
+// thread copies a chunk into one while the DMA engine drains the other, so concurrent callers overlap their host-side
+// copies and their transfers.  Page-locked arrays (FramePipeline, prc_host_alloc / prc_host_register) and asynchronous
+// calls (PRC_FLAG_ASYNC: the caller owns the synchronisation) take the plain cudaMemcpyAsync path.
+constexpr size_t PIN_CHUNK = 4u << 20;
+
+bool host_is_pinned(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_pin(Ctx* c) {
+    if (c->pin_ready) return PRC_OK;
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaHostAlloc(&c->pin[k], PIN_CHUNK, cudaHostAllocPortable));
+        CU(cudaEventCreateWithFlags(&c->pin_ev[k], cudaEventDisableTiming));
+    }
+    c->pin_ready = true;
+    return PRC_OK;
+}
+
+int h2d(Ctx* c, void* dst, const void* src, size_t bytes, unsigned flags) {
+    if ((flags & PRC_FLAG_ASYNC) || bytes < (256u << 10) || host_is_pinned(src)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return PRC_OK;
+    }
+    TRY(ensure_pin(c));
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += PIN_CHUNK, k ^= 1) {
+        const size_t len = std::min(PIN_CHUNK, bytes - off);
+        CU(cudaEventSynchronize(c->pin_ev[k]));           // the transfer that last used this buffer has finished
+        memcpy(c->pin[k], static_cast<const char*>(src) + off, len);
+        CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, c->pin[k], len, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(c->pin_ev[k], c->stream));
+    }
+    return PRC_OK;
+}
+
+int d2h(Ctx* c, void* dst, const void* src, size_t bytes, unsigned flags) {
+    if ((flags & PRC_FLAG_ASYNC) || bytes < (256u << 10) || host_is_pinned(dst)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return PRC_OK;
+    }
+    TRY(ensure_pin(c));
+    const size_t nchunk = (bytes + PIN_CHUNK - 1) / PIN_CHUNK;
+    for (size_t i = 0; i <= nchunk; ++i) {                // transfer of chunk i overlaps the host copy of chunk i - 1
+        if (i < nchunk) {
+            const size_t off = i * PIN_CHUNK, len = std::min(PIN_CHUNK, bytes - off);
+            CU(cudaMemcpyAsync(c->pin[i & 1], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaEventRecord(c->pin_ev[i & 1], c->stream));
+        }
+        if (i >= 1) {
+            const size_t j = i - 1, off = j * PIN_CHUNK, len = std::min(PIN_CHUNK, bytes - off);
+            CU(cudaEventSynchronize(c->pin_ev[j & 1]));
+            memcpy(static_cast<char*>(dst) + off, c->pin[j & 1], len);
+        }
+    }
+    return PRC_OK;
+}
+
 // window (host or device, double or float) -> device float
 int stage_window(Ctx* c, const void* window, long long n, int mem_kind, unsigned flags, const float** win32) {
     *win32 = nullptr;
@@ -1394,7 +1467,7 @@ int stage_window(Ctx* c, const void* window, long long n, int mem_kind, unsigned
             return PRC_OK;
         }
         TRY(c->win32.ensure((size_t)n * sizeof(float)));
-        CU(cudaMemcpyAsync(c->win32.p, window, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->win32.p, window, (size_t)n * sizeof(float), flags));
         *win32 = c->win32.as<float>();
         return PRC_OK;
     }
@@ -1402,7 +1475,7 @@ int stage_window(Ctx* c, const void* window, long long n, int mem_kind, unsigned
     TRY(c->win32.ensure((size_t)n * sizeof(float)));
     if (mem_kind == PRC_MEM_HOST) {
         TRY(c->win64.ensure((size_t)n * sizeof(double)));
-        CU(cudaMemcpyAsync(c->win64.p, window, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->win64.p, window, (size_t)n * sizeof(double), flags));
         w64 = c->win64.as<double>();
     }
     f64_to_f32_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(w64, c->win32.as<float>(), n);
@@ -1420,7 +1493,7 @@ int finish(Ctx* c, unsigned flags) {
 int check_ls_status(Ctx* c, unsigned flags, int nf = 1) {
     if (flags & PRC_FLAG_ASYNC) return PRC_OK;   // caller owns the synchronisation; status stays on the device (prc_ls_status)
     std::vector<int> st((size_t)nf, 0);
-    CU(cudaMemcpyAsync(st.data(), c->status.p, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(st.data(), c->status.p, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost, /*status*/ c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < nf; ++i)
         if (st[i] != 0)
@@ -1593,8 +1666,8 @@ int prc_xambg_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int range_b
         TRY(c->ref.ensure(nb));
         TRY(c->srv.ensure(nb));
         TRY(c->out.ensure(ob));
-        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->ref.p, ref, nb, flags));
+        TRY(h2d(c, c->srv.p, srv, nb, flags));
         dref = c->ref.as<float2>();
         dsrv = c->srv.as<float2>();
         dout = c->out.as<float2>();
@@ -1607,7 +1680,7 @@ int prc_xambg_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int range_b
         const double* t64 = dtaps;
         if (mem_kind == PRC_MEM_HOST) {
             TRY(c->dtaps64.ensure((size_t)ndtaps * sizeof(double)));
-            CU(cudaMemcpyAsync(c->dtaps64.p, dtaps, (size_t)ndtaps * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            TRY(h2d(c, c->dtaps64.p, dtaps, (size_t)ndtaps * sizeof(double), flags));
             t64 = c->dtaps64.as<double>();
         }
         f64_to_f32_kernel<<<ceil_div(ndtaps, 256), 256, 0, c->stream>>>(t64, c->dtaps32.as<float>(), ndtaps);
@@ -1615,7 +1688,7 @@ int prc_xambg_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int range_b
         taps32 = c->dtaps32.as<float>();
     }
     TRY(xambg_device(c, dref, dsrv, n, range_bins, freq_bins, win32, taps32, ndtaps, dout));
-    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, c->out.p, ob, cudaMemcpyDeviceToHost, c->stream));
+    if (mem_kind == PRC_MEM_HOST) TRY(d2h(c, out, c->out.p, ob, flags));
     return finish(c, flags);
 }
 
@@ -1636,8 +1709,8 @@ int prc_ls_filter_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int fil
         TRY(c->ref.ensure(nb));
         TRY(c->srv.ensure(nb));
         TRY(c->clean.ensure(nb));
-        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->ref.p, ref, nb, flags));
+        TRY(h2d(c, c->srv.p, srv, nb, flags));
         dref = c->ref.as<float2>();
         dsrv = c->srv.as<float2>();
         dout = c->clean.as<float2>();
@@ -1645,9 +1718,9 @@ int prc_ls_filter_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int fil
     }
     TRY(ls_device(c, dref, dsrv, n, filter_len, peek, (double)reg, dout, dtaps));
     if (mem_kind == PRC_MEM_HOST) {
-        CU(cudaMemcpyAsync(out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
+        TRY(d2h(c, out, c->clean.p, nb, flags));
         if (taps)
-            CU(cudaMemcpyAsync(taps, c->lstaps.p, (size_t)(filter_len + peek) * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+            TRY(d2h(c, taps, c->lstaps.p, (size_t)(filter_len + peek) * sizeof(float2), flags));
     }
     TRY(check_ls_status(c, flags));
     return finish(c, flags);
@@ -1675,11 +1748,11 @@ int prc_nlms_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_l
         TRY(c->srv.ensure(nb));
         TRY(c->clean.ensure(nb));
         TRY(c->nl_taps.ensure(mb));
-        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->ref.p, ref, nb, flags));
+        TRY(h2d(c, c->srv.p, srv, nb, flags));
         if (init_taps) {
             TRY(c->nl_init.ensure(mb));
-            CU(cudaMemcpyAsync(c->nl_init.p, init_taps, mb, cudaMemcpyHostToDevice, c->stream));
+            TRY(h2d(c, c->nl_init.p, init_taps, mb, flags));
             dinit = c->nl_init.as<float2>();
         }
         dref = c->ref.as<float2>();
@@ -1689,8 +1762,8 @@ int prc_nlms_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int filter_l
     }
     TRY(nlms_device(c, dref, dsrv, n, filter_len, peek, mu, block_len, dinit, dout, dtaps));
     if (mem_kind == PRC_MEM_HOST) {
-        CU(cudaMemcpyAsync(out, c->clean.p, nb, cudaMemcpyDeviceToHost, c->stream));
-        if (taps_out) CU(cudaMemcpyAsync(taps_out, c->nl_taps.p, mb, cudaMemcpyDeviceToHost, c->stream));
+        TRY(d2h(c, out, c->clean.p, nb, flags));
+        if (taps_out) TRY(d2h(c, taps_out, c->nl_taps.p, mb, flags));
     }
     return finish(c, flags);
 }
@@ -1723,12 +1796,12 @@ int prc_nlms_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int n
         TRY(c->clean.ensure(nb * nframes));
         TRY(c->nl_taps.ensure(mb * nframes));
         for (int fr = 0; fr < nframes; ++fr) {
-            CU(cudaMemcpyAsync(c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+            TRY(h2d(c, c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, flags));
+            TRY(h2d(c, c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, flags));
         }
         if (init_taps) {
             TRY(c->nl_init.ensure(mb));
-            CU(cudaMemcpyAsync(c->nl_init.p, init_taps, mb, cudaMemcpyHostToDevice, c->stream));
+            TRY(h2d(c, c->nl_init.p, init_taps, mb, flags));
             dinit = c->nl_init.as<float2>();
         }
         dref = c->ref.as<float2>();
@@ -1741,8 +1814,8 @@ int prc_nlms_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int n
     if (mem_kind == PRC_MEM_HOST) {
         const size_t fs = (size_t)(nframes > 1 ? frame_stride : n);
         for (int fr = 0; fr < nframes; ++fr)
-            CU(cudaMemcpyAsync(out + fr * fs, c->clean.as<float2>() + (size_t)fr * n, nb, cudaMemcpyDeviceToHost, c->stream));
-        if (taps_out) CU(cudaMemcpyAsync(taps_out, c->nl_taps.p, mb * nframes, cudaMemcpyDeviceToHost, c->stream));
+            TRY(d2h(c, out + fr * fs, c->clean.as<float2>() + (size_t)fr * n, nb, flags));
+        if (taps_out) TRY(d2h(c, taps_out, c->nl_taps.p, mb * nframes, flags));
     }
     return finish(c, flags);
 }
@@ -1772,8 +1845,8 @@ int prc_xambg_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int 
         TRY(c->srv.ensure(nb * nframes));
         TRY(c->out.ensure(ob * nframes));
         for (int fr = 0; fr < nframes; ++fr) {
-            CU(cudaMemcpyAsync(c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+            TRY(h2d(c, c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, flags));
+            TRY(h2d(c, c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, flags));
         }
         dref = c->ref.as<float2>();
         dsrv = c->srv.as<float2>();
@@ -1791,7 +1864,7 @@ int prc_xambg_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int 
             TRY(xambg_device(c, dref + (size_t)fr * bt.stride, dsrv + (size_t)fr * bt.stride, n, range_bins, freq_bins, win32,
                              nullptr, 0, dout + (size_t)fr * freq_bins * (range_bins + 1)));
     }
-    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, c->out.p, ob * nframes, cudaMemcpyDeviceToHost, c->stream));
+    if (mem_kind == PRC_MEM_HOST) TRY(d2h(c, out, c->out.p, ob * nframes, flags));
     return finish(c, flags);
 }
 
@@ -1827,8 +1900,8 @@ int prc_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframe
         TRY(c->out.ensure(ob * nframes));
         if (cleaned_out) TRY(c->clean.ensure(nb * nframes));
         for (int fr = 0; fr < nframes; ++fr) {
-            CU(cudaMemcpyAsync(c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync(c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, cudaMemcpyHostToDevice, c->stream));
+            TRY(h2d(c, c->ref.as<float2>() + (size_t)fr * n, ref + (size_t)fr * bt.stride, nb, flags));
+            TRY(h2d(c, c->srv.as<float2>() + (size_t)fr * n, srv + (size_t)fr * bt.stride, nb, flags));
         }
         dref = c->ref.as<float2>();
         dsrv = c->srv.as<float2>();
@@ -1841,16 +1914,16 @@ int prc_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframe
     TRY(stage_window(c, window, n, mem_kind, flags, &win32));
     TRY(frame_device(c, dref, dsrv, n, bt, filter_len, peek, (double)reg, range_bins, freq_bins, win32, dmap, dtaps, dclean));
     if (mem_kind == PRC_MEM_HOST) {
-        CU(cudaMemcpyAsync(out_maps, c->out.p, ob * nframes, cudaMemcpyDeviceToHost, c->stream));
+        TRY(d2h(c, out_maps, c->out.p, ob * nframes, flags));
         if (taps_out) {
             if (nframes > 1 && !(ls_fft_plan(c, n, M, nframes).on && caf_fft_plan(n, range_bins, freq_bins, n / freq_bins + 1, n / freq_bins, true, M).on))
                 return fail(PRC_E_INVALID, "taps_out with host pointers and nframes > 1 needs the FFT-domain path");
-            CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)nframes * M * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+            TRY(d2h(c, taps_out, c->lstaps.p, (size_t)nframes * M * sizeof(float2), flags));
         }
         if (cleaned_out) {
             const size_t fs = (size_t)(nframes > 1 ? frame_stride : n);
             for (int fr = 0; fr < nframes; ++fr)
-                CU(cudaMemcpyAsync(cleaned_out + fr * fs, c->clean.as<float2>() + (size_t)fr * n, nb, cudaMemcpyDeviceToHost, c->stream));
+                TRY(d2h(c, cleaned_out + fr * fs, c->clean.as<float2>() + (size_t)fr * n, nb, flags));
         }
     }
     TRY(check_ls_status(c, flags, nframes));
@@ -1870,7 +1943,7 @@ int prc_ls_status(int device, void* stream, int* status, int nframes) {
     TRY(get_ctx(device, stream, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     if (c->status.cap < (size_t)nframes * sizeof(int)) return fail(PRC_E_INVALID, "no LS solve of %d frames has run on this stream", nframes);
-    CU(cudaMemcpyAsync(status, c->status.p, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(status, c->status.p, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, /*status*/ c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return PRC_OK;
 }
@@ -1923,8 +1996,8 @@ int prc_ls_multiple_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int f
     if (mem_kind == PRC_MEM_HOST) {
         TRY(c->ref.ensure(nb));
         TRY(c->srv.ensure(nb));
-        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->ref.p, ref, nb, flags));
+        TRY(h2d(c, c->srv.p, srv, nb, flags));
         dref = c->ref.as<float2>();
         dsrv = c->srv.as<float2>();
         dtaps = nullptr;
@@ -1941,8 +2014,8 @@ int prc_ls_multiple_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int f
         cur = dst;
     }
     if (mem_kind == PRC_MEM_HOST) {
-        CU(cudaMemcpyAsync(out, cur, nb, cudaMemcpyDeviceToHost, c->stream));
-        if (taps_last) CU(cudaMemcpyAsync(taps_last, c->lstaps.p, (size_t)M * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+        TRY(d2h(c, out, cur, nb, flags));
+        if (taps_last) TRY(d2h(c, taps_last, c->lstaps.p, (size_t)M * sizeof(float2), flags));
     }
     return finish(c, flags);
 }
@@ -1963,12 +2036,12 @@ int prc_iq_mix_c64(const void* in, int in_kind, int64_t n, int mode, double fc, 
     if (mem_kind == PRC_MEM_HOST) {
         TRY(c->fe_in.ensure(iq_bytes(in_kind, n)));
         TRY(c->fe_out.ensure((size_t)n * sizeof(float2)));
-        CU(cudaMemcpyAsync(c->fe_in.p, in, iq_bytes(in_kind, n), cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->fe_in.p, in, iq_bytes(in_kind, n), flags));
         din = c->fe_in.p;
         dout = c->fe_out.as<float2>();
     }
     TRY(mix_device(c, make_mix(din, in_kind, n, mode, fc, fs, phase_offset), dout));
-    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    if (mem_kind == PRC_MEM_HOST) TRY(d2h(c, out, dout, (size_t)n * sizeof(float2), flags));
     return finish(c, flags);
 }
 
@@ -2000,13 +2073,13 @@ int prc_frontend_c64(const void* in, int in_kind, int64_t n, int mode, double fc
     if (mem_kind == PRC_MEM_HOST) {
         TRY(c->fe_in.ensure(iq_bytes(in_kind, n)));
         TRY(c->fe_out.ensure((size_t)g.n_out * sizeof(float2)));
-        CU(cudaMemcpyAsync(c->fe_in.p, in, iq_bytes(in_kind, n), cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->fe_in.p, in, iq_bytes(in_kind, n), flags));
         din = c->fe_in.p;
         dout = c->fe_out.as<float2>();
     }
     long long n_out = 0;
     TRY(resample_device(c, make_mix(din, in_kind, n, mode, fc, fs, phase_offset), up, down, h, nh, dout, &n_out));
-    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, dout, (size_t)n_out * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    if (mem_kind == PRC_MEM_HOST) TRY(d2h(c, out, dout, (size_t)n_out * sizeof(float2), flags));
     return finish(c, flags);
 }
 
@@ -2027,15 +2100,15 @@ int prc_cfar2d_f32(const void* x, int rows, int cols, int fw, int gw, const floa
     if (mem_kind == PRC_MEM_HOST) {
         const size_t inb = cells * (cplx ? sizeof(float2) : sizeof(float));
         TRY(c->cf_in.ensure(inb));
-        CU(cudaMemcpyAsync(c->cf_in.p, x, inb, cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->cf_in.p, x, inb, flags));
         dx = c->cf_in.p;
         if (cr_out) { TRY(c->cf_cr.ensure(cells * sizeof(float))); dcr = c->cf_cr.as<float>(); }
         if (det_out) { TRY(c->cf_det.ensure(cells)); ddet = c->cf_det.as<uint8_t>(); }
     }
     TRY(cfar_device(c, dx, cplx, rows, cols, fw, gw, thresh, dcr, ddet));
     if (mem_kind == PRC_MEM_HOST) {
-        if (cr_out) CU(cudaMemcpyAsync(cr_out, dcr, cells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (det_out) CU(cudaMemcpyAsync(det_out, ddet, cells, cudaMemcpyDeviceToHost, c->stream));
+        if (cr_out) TRY(d2h(c, cr_out, dcr, cells * sizeof(float), flags));
+        if (det_out) TRY(d2h(c, det_out, ddet, cells, flags));
     }
     return finish(c, flags);
 }
@@ -2058,14 +2131,14 @@ int prc_direct_xambg_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int 
         TRY(c->ref.ensure(nb));
         TRY(c->srv.ensure(nb));
         TRY(c->out.ensure(ob));
-        CU(cudaMemcpyAsync(c->ref.p, ref, nb, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->srv.p, srv, nb, cudaMemcpyHostToDevice, c->stream));
+        TRY(h2d(c, c->ref.p, ref, nb, flags));
+        TRY(h2d(c, c->srv.p, srv, nb, flags));
         dref = c->ref.as<float2>();
         dsrv = c->srv.as<float2>();
         dout = c->out.as<float2>();
     }
     TRY(direct_xambg_device(c, dref, dsrv, n, range_bins, freq_bins, sample_rate, dout));
-    if (mem_kind == PRC_MEM_HOST) CU(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, c->stream));
+    if (mem_kind == PRC_MEM_HOST) TRY(d2h(c, out, dout, ob, flags));
     return finish(c, flags);
 }
 

@@ -51,6 +51,29 @@ def test_xambg_large_shapes_sampled_columns(n, F, R, win, both_paths):
     assert e <= TOL, e
 
 
+@pytest.mark.parametrize("n,F,R,fl", [
+    (2 ** 18, 64, 1200, 0),            # many range bins: segments of L - R samples (L = 2048 or 4096 by cost)
+    (2 ** 18, 32, 700, 700),           # fused frame with R + M - 1 = 1409: 639-sample segments at L = 2048
+    (2 ** 17, 16, 1500, 1500),         # L = 4096 transforms (R + M - 1 = 3009)
+])
+def test_long_range_and_long_filter_take_the_larger_transforms(n, F, R, fl, both_paths):
+    from oracle import xambg_oracle as xo
+    ref, srv = synth.make_frame(n, "P0", frame=23)
+    w = signal.get_window(("kaiser", 5.0), n)
+    if fl == 0:
+        got = prb.fast_xambg(ref, srv, R, F, n, w)
+        want = xo.fast_xambg_oracle(ref, srv, R, F, n, w)
+        e = G.rel_inf(got, want)
+        assert e <= TOL, e
+    else:
+        from passiveradar_b200.frames import FramePipeline
+        got = FramePipeline(n, R, F, filter_len=fl, batch=2, nslots=1).process(ref, srv)
+        want = prb.fast_xambg(ref, prb.LS_Filter(ref, srv, fl), R, F, n, w)
+        e = G.rel_inf(got, want)
+        assert e <= 2e-6, e
+    record_parity(f"long/n{n}_F{F}_R{R}_fl{fl}/{both_paths}", E=e)
+
+
 def test_ls_config4_size_and_readme_shape(both_paths):
     from oracle import clutter_oracle as co
     for n, fl in ((2 ** 21, 400), (524288, 175), (10 ** 6, 300)):
