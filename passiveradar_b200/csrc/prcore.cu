@@ -526,7 +526,7 @@ struct Batch {
 };
 
 inline int r3_index(int r3) { return r3 == 4 ? 0 : (r3 == 8 ? 1 : 2); }
-inline size_t fft_smem(int r3) { return (size_t)(2 * 16 * 17 * r3 + 256 * r3 + 16 * r3) * sizeof(float2); }
+inline size_t fft_smem(int r3) { return (size_t)(2 * 16 * 17 * r3 + 256 * r3 + 16 * r3) * sizeof(float2); }   // fft::Geo<R3>::SMEM_FLOAT2: exchange buffers + twiddles, no staging
 inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // R3 = 4 / 8 / 16  <->  L = 1024 / 2048 / 4096
