@@ -14,7 +14,7 @@ import threading
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libprcore.so")
+LIB_PATH = os.environ.get("PRC_LIBRARY") or os.path.join(_PKG, "libprcore.so")     # PRC_LIBRARY: A/B builds during development
 
 PRC_OK = 0
 PRC_E_INVALID = -1
@@ -101,7 +101,7 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if build_if_missing:
+        if build_if_missing and not os.environ.get("PRC_LIBRARY"):
             # rebuild when the library is missing OR older than any source/header (a stale .so after an edit is
             # the worst kind of bug); a no-op when up to date.  Without nvcc an existing library is used as is
             # (the GPU box receives the library built here).
