@@ -179,6 +179,7 @@ int g_stream = 1;          // persistent pipelined lag-correlation kernel (PRC_S
 int g_packed = 1;          // FFMA2 kernels (PRC_PACKED=0 selects the scalar-FFMA variant for A/B runs)
 std::atomic<int> g_fft{1};            // FFT-domain correlation / overlap-save kernels (fftcorr.cuh); PRC_FFT=0: tcgen05 / FP32 direct form
 std::atomic<int> g_fft_min_n{8192};   // ... for channels of at least this many samples (PRC_FFT_MIN_N)
+std::atomic<int> g_caf_wave{0};       // 1: CAF kernel grid = one wave of CTAs walking several Doppler blocks (measured 4 % slower than one CTA per block)
 std::once_flag g_env_once;
 
 // Workspaces of a thread that called with stream == NULL.  They are released when the thread exits (dask's thread pool
@@ -684,7 +685,11 @@ int caf_fft(Ctx* c, const CafFftPlan& pl, const float2* ref, const float2* srv, 
     p.n = (int)n; p.R = R; p.F = F; p.M = M; p.peek = peek;
     p.D = D; p.c0 = c0; p.ntaps = (int)ntaps; p.Bmax = pl.Bmax;
     p.P = c->fftP.as<float2>(); p.HT = pl.HT; p.tw = tw;
-    const dim3 grid(F, bt.nf);
+    // one wave of CTAs for the whole batch (3 resident per SM): a CTA walks several Doppler blocks of its frame, so the
+    // twiddle tables are staged once per CTA and there is no partially filled last wave
+    int gx = F;
+    if (g_caf_wave.load()) gx = (int)std::max<long long>(1, std::min<long long>(F, 3ll * c->nsm / bt.nf));
+    const dim3 grid(gx, bt.nf);
     {
         ProfScope ps(c, K_LAGCORR_CAF);
         if (wp) { PRC_R3_SWITCH(pl.r3, (fftc::caf_fft_kernel<R3, true><<<grid, 16 * R3, fftc::caf_smem_float2<R3>() * sizeof(float2), c->stream>>>(p))); }
@@ -1954,6 +1959,7 @@ int prc_set_option(const char* name, int value) {
     const std::string k(name);
     if (k == "fft") g_fft.store(value);
     else if (k == "fft_min_n") g_fft_min_n.store(value);
+    else if (k == "caf_wave") g_caf_wave.store(value);
     else return fail(PRC_E_INVALID, "unknown option '%s'", name);
     return PRC_OK;
 }
@@ -1964,6 +1970,7 @@ int prc_get_option(const char* name, int* value) {
     const std::string k(name);
     if (k == "fft") *value = g_fft.load();
     else if (k == "fft_min_n") *value = g_fft_min_n.load();
+    else if (k == "caf_wave") *value = g_caf_wave.load();
     else return fail(PRC_E_INVALID, "unknown option '%s'", name);
     return PRC_OK;
 }

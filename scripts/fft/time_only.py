@@ -16,6 +16,10 @@ fr = [synth.make_frame(n, "P1", i) for i in range(4)]
 ref_d = torch.from_numpy(np.stack([fr[i % 4][0] for i in range(B)])).to(dev)
 srv_d = torch.from_numpy(np.stack([fr[i % 4][1] for i in range(B)])).to(dev)
 maps = torch.empty((B, F, R + 1), dtype=torch.complex64, device=dev)
+if len(sys.argv) > 1:
+    for kv in sys.argv[1:]:
+        k, v = kv.split("=")
+        _lib.set_option(k, int(v))
 for batch, slots in ((16, 3), (16, 1)):
     pipe = FramePipeline(n, R, F, batch=batch, nslots=slots)
     for _ in range(3):
