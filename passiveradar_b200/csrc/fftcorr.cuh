@@ -59,19 +59,18 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // element with immediate offsets (the index arithmetic of the general case costs as many issue slots as the copies).
 template <int T, bool FULL>
 __device__ __forceinline__ void stage_sig(float2* stg, int t, const float2* __restrict__ sig, long long base, int len,
-                                          int n, int linear, int vlo = 0) {
+                                          int n, int linear) {
     if (base >= 0 && base + 16 * T <= n) {
         const float2* p0 = sig + base + t;
         float2* d0 = stg + t;
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1)
-            if (FULL || n1 * T < len)       // rows beyond len: not staged
-                cp_async8(d0 + n1 * T, p0 + n1 * T, FULL || (n1 * T + t < len && n1 * T + t >= vlo));
+            if (FULL || n1 * T < len) cp_async8(d0 + n1 * T, p0 + n1 * T, FULL || n1 * T + t < len);   // rows beyond len: not staged
         return;
     }
-    int lo = vlo, hi = FULL ? 16 * T : len, wrap = 0x7fffffff;
+    int lo = 0, hi = FULL ? 16 * T : len, wrap = 0x7fffffff;
     if (linear) {                                   // valid i: 0 <= base + i < n
-        lo = base < 0 ? max(vlo, (int)(-base)) : vlo;
+        lo = base < 0 ? (int)(-base) : 0;
         const long long h = (long long)n - base;
         hi = h < (long long)hi ? (h < 0 ? 0 : (int)h) : hi;
     } else {
@@ -389,223 +388,6 @@ __global__ void __launch_bounds__(16 * R3) caf_fft_kernel(const __grid_constant_
             if (d <= p.R) row[d] = make_float2(acc[n1].x * inv, acc[n1].y * inv);
         }
     }
-}
-
-// =====================================================================================================================
-// Shared-spectra frame: the LS lag sums and the CAF use ONE segmentation of the channel (the CAF's: Doppler blocks cut
-// into segments of <= bmax samples, table built on the host, prcore.cu: build_seg_table / scripts/fft/model.py:
-// segment_table) and share the spectra of each segment's reference / surveillance windows through HBM:
-//
-//   window of segment s:  R' = ref[a .. a+L),  S' = srv[a-peek .. a-peek+L),  a = i0 - (M-1-peek)
-//   lsspec_fft_kernel     X_u = the segment's LS-owned reference samples (zero elsewhere, at window position off + q):
-//                         accC += X_u conj(R'), accX += X_u conj(S') (lag m at output index off + m, off = M-1-peek);
-//                         R' and S' are written to `spec` on the way: 3 transforms per segment
-//   (levinson, taps_spectrum with the taps at positions 0..M-1: no shift)
-//   cafspec_fft_kernel    X_w = windowed reference segment; acc += X_w conj(S' - R' W) with S', R' READ BACK (their loads
-//                         fly during the transform of X_w); lag d at output index (M-1) + d: 1 transform per segment
-//
-// 4 transforms per segment instead of 3 (LS, per 1737 samples) + 3 (CAF, per 1366 samples): 3 330 instead of 4 682 per
-// config-2 frame, for 25 MB of spectra written and read back per frame.
-struct Seg { int i0, ln, mlo, mhi; };       // CAF: ref[i0 : i0+ln) (ln = 0: none); LS owns ref[i0+mlo : i0+mhi)
-
-struct LsSpecParams {
-    const float2* ref;
-    const float2* srv;
-    long long frame_stride;
-    int n, M, peek, off;       // off = M - 1 - peek
-    const Seg* segs;
-    int nseg;
-    float2* spec;              // [frame][nseg][2][L]  (0: R', 1: S'), permuted order
-    float2* partial;           // [frame][2][gridDim.x][HT]
-    int HT;
-    const float2* tw;
-};
-
-// resident CTAs per SM the register allocation must allow (168 registers per thread)
-template <int R3> constexpr int kResident() { return R3 == 4 ? 6 : (R3 == 8 ? 3 : 1); }
-
-template <int R3>
-__global__ void __launch_bounds__(16 * R3, kResident<R3>()) lsspec_fft_kernel(const __grid_constant__ LsSpecParams p) {
-    using G = fft::Geo<R3>;
-    extern __shared__ __align__(16) float2 sm[];
-    const int t = threadIdx.x;
-    const fft::Smem<R3> S(sm);
-    float2* stg = sm + G::SMEM_FLOAT2;
-    const float2* ref = p.ref + (size_t)blockIdx.y * p.frame_stride;
-    const float2* srv = p.srv + (size_t)blockIdx.y * p.frame_stride;
-    float2* spec = p.spec + (size_t)blockIdx.y * p.nseg * 2 * G::L;
-    const int nmine = ((int)blockIdx.x < p.nseg) ? (p.nseg - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nitems = 3 * nmine;
-
-    auto issue = [&](int it) {
-        const int q = it / 3, kind = it - 3 * q;
-        const Seg sg = p.segs[blockIdx.x + q * gridDim.x];
-        const long long a = (long long)sg.i0 - p.off;
-        if (kind == 0) stage_sig<G::T, false>(stg, t, ref, sg.i0, sg.mhi, p.n, 0, sg.mlo);
-        else if (kind == 1) stage_sig<G::T, true>(stg, t, ref, a, G::L, p.n, 0);
-        else stage_sig<G::T, true>(stg, t, srv, a - p.peek, G::L, p.n, 0);
-        cp_async_commit();
-    };
-
-    if (nitems) issue(0);
-    fft::stage_twiddles<R3>(sm, p.tw, t);
-    __syncthreads();
-
-    float2 accC[16], accX[16], X[16], v[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) accC[r] = accX[r] = X[r] = make_float2(0.f, 0.f);
-#pragma unroll 1
-    for (int it = 0; it < nitems; ++it) {
-        const int q = it / 3, kind = it - 3 * q;
-        const int sidx = blockIdx.x + q * gridDim.x;
-        const Seg sg = p.segs[sidx];
-        if (kind == 0) fetch_staged<G::T, false>(v, stg, t, sg.mhi);
-        else fetch_staged<G::T, true>(v, stg, t, G::L);
-        fft::fft_n2p<R3>(v, t, S, [&] { if (it + 1 < nitems) issue(it + 1); });
-        if (kind == 0) {
-#pragma unroll
-            for (int r = 0; r < 16; ++r) X[r] = v[r];
-        } else {
-            if (sg.ln > 0) {                                // the CAF reads this window back
-                float2* dst = spec + ((size_t)sidx * 2 + (kind - 1)) * G::L + t;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) dst[r * G::T] = v[r];
-            }
-            if (kind == 1) {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) cmacc(accC[r], X[r], v[r]);
-            } else {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) cmacc(accX[r], X[r], v[r]);
-            }
-        }
-    }
-    const float inv = 1.0f / (float)G::L;
-#pragma unroll 1
-    for (int w = 0; w < 2; ++w) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = w ? accX[r] : accC[r];
-        fft::fft_p2n<R3>(v, t, S);
-        float2* row = p.partial + ((size_t)(blockIdx.y * 2 + w) * gridDim.x + blockIdx.x) * p.HT;
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const int m = n1 * G::T + t - p.off;            // lag m sits at output index off + m
-            if (m >= 0 && m < p.M) row[m] = make_float2(v[n1].x * inv, v[n1].y * inv);
-        }
-    }
-}
-
-struct CafSpecParams {
-    const float2* ref;
-    long long frame_stride;
-    const float* win;          // n floats shared by all frames, or NULL
-    const float2* wp;          // [frame][L]: spectrum of the taps at positions 0..M-1 (permuted order)
-    const float2* spec;        // [frame][nseg][2][L]
-    const Seg* segs;
-    const int* blk;            // [F + 1]: segments of Doppler block j are blk[j] .. blk[j+1]
-    int nseg, n, R, F, M;
-    float2* P;                 // [frame][F][HT]
-    int HT;
-    const float2* tw;
-};
-
-// shared memory: [fft::Smem | staging L float2 | window staging L float]
-template <int R3>
-__global__ void __launch_bounds__(16 * R3, kResident<R3>()) cafspec_fft_kernel(const __grid_constant__ CafSpecParams p) {
-    using G = fft::Geo<R3>;
-    extern __shared__ __align__(16) float2 sm[];
-    const int t = threadIdx.x;
-    const fft::Smem<R3> S(sm);
-    float2* stg = sm + G::SMEM_FLOAT2;
-    float* wst = reinterpret_cast<float*>(stg + G::L);
-    const float2* ref = p.ref + (size_t)blockIdx.y * p.frame_stride;
-    const float2* wp = p.wp + (size_t)blockIdx.y * G::L + t;
-    const float2* spec = p.spec + (size_t)blockIdx.y * p.nseg * 2 * G::L + t;
-    const float inv = 1.0f / (float)G::L;
-    const int j = blockIdx.x;
-    const int s0 = p.blk[j], s1 = p.blk[j + 1];
-
-    auto issue = [&](int sidx) {
-        const Seg sg = p.segs[sidx];
-        stage_sig<G::T, false>(stg, t, ref, sg.i0, sg.ln, p.n, 0);
-        if (p.win) {
-            const float* w0 = p.win + sg.i0 + t;
-#pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1)
-                if (n1 * G::T < sg.ln) cp_async4(wst + t + n1 * G::T, w0 + n1 * G::T, n1 * G::T + t < sg.ln);
-        }
-        cp_async_commit();
-    };
-    if (s1 > s0) issue(s0);
-    fft::stage_twiddles<R3>(sm, p.tw, t);
-    __syncthreads();
-
-    float2 acc[16], v[16], sr[16], ss[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll 1
-    for (int sidx = s0; sidx < s1; ++sidx) {
-        const Seg sg = p.segs[sidx];
-        const float2* sp = spec + (size_t)sidx * 2 * G::L;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {                      // the windows' spectra: in flight during the transform below
-            sr[r] = __ldcs(sp + r * G::T);
-            ss[r] = __ldcs(sp + G::L + r * G::T);
-        }
-        fetch_staged<G::T, false>(v, stg, t, sg.ln);
-        if (p.win) {
-#pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                if (n1 * G::T < sg.ln) {
-                    const float w = wst[t + n1 * G::T];
-                    v[n1].x *= w;
-                    v[n1].y *= w;
-                }
-            }
-        }
-        fft::fft_n2p<R3>(v, t, S, [&] { if (sidx + 1 < s1) issue(sidx + 1); });
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {                      // acc += X_w conj(S' - R' W)
-            const float2 y = cmul(sr[r], __ldg(wp + r * G::T));
-            cmacc(acc[r], v[r], make_float2(ss[r].x - y.x, ss[r].y - y.y));
-        }
-    }
-    if (s1 > s0) fft::fft_p2n<R3>(acc, t, S);
-    float2* row = p.P + ((size_t)blockIdx.y * p.F + j) * p.HT;
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int d = n1 * G::T + t - (p.M - 1);            // lag d sits at output index (M - 1) + d
-        if (d >= 0 && d <= p.R) row[d] = make_float2(acc[n1].x * inv, acc[n1].y * inv);
-    }
-}
-
-// taps at positions 0..M-1 (no circular shift): W for the shared-spectra frame
-struct TapSpec0Params {
-    const float2* taps;        // [frame][M]
-    int M;
-    float2* wp;                // [frame][L], permuted order
-    const float2* tw;
-};
-
-template <int R3>
-__global__ void __launch_bounds__(16 * R3) taps_spectrum0_kernel(const __grid_constant__ TapSpec0Params p) {
-    using G = fft::Geo<R3>;
-    extern __shared__ __align__(16) float2 sm[];
-    const int t = threadIdx.x;
-    const fft::Smem<R3> S(sm);
-    fft::stage_twiddles<R3>(sm, p.tw, t);
-    __syncthreads();
-    const float2* taps = p.taps + (size_t)blockIdx.x * p.M;
-    float2 v[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        const int k = n1 * G::T + t;
-        v[n1] = (k < p.M) ? taps[k] : make_float2(0.f, 0.f);
-    }
-    fft::fft_n2p<R3>(v, t, S);
-    float2* wp = p.wp + (size_t)blockIdx.x * G::L;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) wp[r * G::T + t] = v[r];
 }
 
 }  // namespace fftc

@@ -138,9 +138,6 @@ struct Ctx {
     bool pin_ready = false;
     DBuf fft_tw[3], wp_fir, wp_caf, fftP;     // FFT-domain path: twiddle tables (L = 1024 / 2048 / 4096), taps spectra, CAF block sums
     bool fft_tw_ready[3] = {false, false, false};
-    DBuf seg_tab, seg_blk, spec;              // shared-spectra frame: segment table, block offsets, window spectra
-    long long seg_key[6] = {0, 0, 0, 0, 0, 0};  // (n, F, R, M, peek, r3) the table was built for
-    int seg_count = 0;
     std::vector<ProfRec> recs;
     void release() {
         cudaSetDevice(device);
@@ -151,8 +148,7 @@ struct Ctx {
         clean2.release();
         for (DBuf& b : fft_tw) b.release();
         for (bool& r : fft_tw_ready) r = false;
-        for (DBuf* b : {&wp_fir, &wp_caf, &fftP, &seg_tab, &seg_blk, &spec}) b->release();
-        seg_key[0] = 0;
+        for (DBuf* b : {&wp_fir, &wp_caf, &fftP}) b->release();
         for (DBuf* b : {&fe_in, &fe_mid, &fe_out, &fe_hp, &fe_ends, &cf_in, &cf_cr, &cf_det, &cf_part}) b->release();
         for (DBuf* b : {&refw, &ref, &srv, &out, &clean, &partial, &win32, &win64, &dtaps32, &dtaps64, &lstaps,
                         &tw, &pbuf, &status, &nl_init, &nl_taps})
@@ -183,7 +179,6 @@ int g_stream = 1;          // persistent pipelined lag-correlation kernel (PRC_S
 int g_packed = 1;          // FFMA2 kernels (PRC_PACKED=0 selects the scalar-FFMA variant for A/B runs)
 std::atomic<int> g_fft{1};            // FFT-domain correlation / overlap-save kernels (fftcorr.cuh); PRC_FFT=0: tcgen05 / FP32 direct form
 std::atomic<int> g_fft_min_n{8192};   // ... for channels of at least this many samples (PRC_FFT_MIN_N)
-std::atomic<int> g_share{1};          // fused frames: LS and CAF share one segmentation and the windows' spectra (0: separate kernels)
 std::atomic<int> g_caf_wave{0};       // 1: CAF kernel grid = one wave of CTAs walking several Doppler blocks (measured 4 % slower than one CTA per block)
 std::once_flag g_env_once;
 
@@ -227,7 +222,6 @@ void read_env() {
     if (const char* e = getenv("PRC_TILE")) g_tile = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("PRC_FFT")) g_fft.store(atoi(e));
     if (const char* e = getenv("PRC_FFT_MIN_N")) g_fft_min_n.store(atoi(e));
-    if (const char* e = getenv("PRC_SHARE")) g_share.store(atoi(e));
 }
 
 int set_kernel_attrs(int device) {
@@ -264,10 +258,7 @@ int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(fftc::taps_spectrum_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));        \
     CU(cudaFuncSetAttribute(fftc::fir_fft_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));              \
     CU(cudaFuncSetAttribute(fftc::caf_fft_kernel<R3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));       \
-    CU(cudaFuncSetAttribute(fftc::caf_fft_kernel<R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));        \
-    CU(cudaFuncSetAttribute(fftc::lsspec_fft_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));           \
-    CU(cudaFuncSetAttribute(fftc::cafspec_fft_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));          \
-    CU(cudaFuncSetAttribute(fftc::taps_spectrum0_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(fftc::caf_fft_kernel<R3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     PRC_FFT_ATTRS(4)
     PRC_FFT_ATTRS(8)
     PRC_FFT_ATTRS(16)
@@ -707,198 +698,14 @@ int caf_fft(Ctx* c, const CafFftPlan& pl, const float2* ref, const float2* srv, 
     return check_launch("caf_fft_kernel");
 }
 
+// --------------------------------------------------------------------------- device pipelines
+// All pointers are device pointers; everything is enqueued on c->stream.
+
 int decimator_offset(long long ntaps, long long D) {   // resample_poly alignment, up = 1
     const long long half = (ntaps - 1) / 2;
     const long long pre_pad = D - half % D;
     const long long pre_remove = (half + pre_pad) / D;
     return (int)(pre_remove * D - pre_pad);
-}
-
-// ---- shared-spectra frame (fftcorr.cuh: lsspec_fft_kernel / cafspec_fft_kernel)
-struct SharedPlan {
-    bool on = false;
-    int r3 = 8, off = 0, bmax = 0, ncta = 0, HT = 0, HTP = 0, c0 = 0;
-    long long D = 0;
-};
-
-SharedPlan shared_plan(const Ctx* c, long long n, int R, int F, int M, int peek, int nf) {
-    SharedPlan pl;
-    if (!g_fft.load() || !g_share.load() || n < g_fft_min_n.load() || M < 1 || M > 2048 || F < 1) return pl;
-    const long long D = n / F;
-    if (D < 32) return pl;
-    const int off = M - 1 - peek;
-    if (off < 0) return pl;
-    double best = 0.0;
-    for (int r3 : {4, 8, 16}) {
-        const int L = 256 * r3;
-        const long long bmax = std::min<long long>((long long)L - R - (M - 1), (long long)L - off - (M - 1));
-        if (bmax < L / 4 || n < 2 * L) continue;
-        const long long nseg = (D + 1 + bmax - 1) / bmax;
-        const double cost = (double)(nseg * 4 + 1) * L * ilog2(L);
-        if (!pl.on || cost < best) { pl.on = true; pl.r3 = r3; pl.bmax = (int)bmax; best = cost; }
-    }
-    if (!pl.on) return pl;
-    pl.off = off;
-    pl.D = D;
-    pl.c0 = decimator_offset(D + 1, D);
-    pl.HT = (M + 1) & ~1;
-    pl.HTP = (R + 2) & ~1;
-    pl.ncta = (int)std::max<long long>(1, 3ll * c->nsm / nf);
-    return pl;
-}
-
-// Doppler block j sums samples [lo_j, hi_j) (boxcar of D + 1 taps: neighbouring blocks share one sample); every block is
-// cut into segments of <= bmax samples; the LS sums own every sample of [0, n) exactly once (the shared boundary sample
-// belongs to the earlier block, the tail beyond the last block gets LS-only segments).  Twin: scripts/fft/model.py.
-void build_seg_table(long long n, int F, const SharedPlan& pl, std::vector<fftc::Seg>* segs, std::vector<int>* blk) {
-    segs->clear();
-    blk->assign(1, 0);
-    long long owned = 0;
-    for (int j = 0; j < F; ++j) {
-        long long lo = (long long)j * pl.D + pl.c0 - pl.D, hi = (long long)j * pl.D + pl.c0 + 1;
-        if (lo < 0) lo = 0;
-        if (hi > n) hi = n;
-        if (hi > lo) {
-            const long long nseg = (hi - lo + pl.bmax - 1) / pl.bmax;
-            const long long Bs = (hi - lo + nseg - 1) / nseg;
-            for (long long q = 0; q < nseg; ++q) {
-                const long long i0 = lo + q * Bs;
-                const long long ln = std::min(Bs, hi - i0);
-                const long long mlo = std::max<long long>(owned - i0, 0);
-                const long long mhi = std::max(ln, mlo);
-                segs->push_back(fftc::Seg{(int)i0, (int)ln, (int)mlo, (int)mhi});
-                owned = std::max(owned, i0 + ln);
-            }
-        }
-        blk->push_back((int)segs->size());
-    }
-    while (owned < n) {
-        const long long ln = std::min<long long>(pl.bmax, n - owned);
-        segs->push_back(fftc::Seg{(int)owned, 0, 0, (int)ln});
-        owned += ln;
-    }
-}
-
-int shared_table(Ctx* c, long long n, int R, int F, int M, int peek, const SharedPlan& pl) {
-    const long long key[6] = {n, F, R, M, peek, pl.r3};
-    bool same = c->seg_key[0] != 0;
-    for (int k = 0; same && k < 6; ++k) same = c->seg_key[k] == key[k];
-    if (same) return PRC_OK;
-    std::vector<fftc::Seg> segs;
-    std::vector<int> blk;
-    build_seg_table(n, F, pl, &segs, &blk);
-    c->seg_key[0] = 0;
-    TRY(c->seg_tab.ensure(segs.size() * sizeof(fftc::Seg)));
-    TRY(c->seg_blk.ensure(blk.size() * sizeof(int)));
-    CU(cudaMemcpyAsync(c->seg_tab.p, segs.data(), segs.size() * sizeof(fftc::Seg), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->seg_blk.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));       // the vectors are stack-lifetime host buffers
-    c->seg_count = (int)segs.size();
-    for (int k = 0; k < 6; ++k) c->seg_key[k] = key[k];
-    return PRC_OK;
-}
-
-int doppler_stage(Ctx* c, const float2* src, int nchunk, int HT, long long ntaps, long long d_per_cta, const float2* bnd_x,
-                  const float2* bnd_s, const float* bnd_w, long long D, int c0, long long n, int R, int F, float2* out, Batch bt);
-
-// maps (and taps) of nf frames: lsspec -> levinson -> taps spectrum -> cafspec -> Doppler FFT
-int shared_frames(Ctx* c, const SharedPlan& pl, const float2* ref, const float2* srv, long long n, Batch bt, int filter_len,
-                  int peek, double reg, int R, int F, const float* win32, float2* maps, float2* taps_out) {
-    const int M = filter_len + peek;
-    const int L = 256 * pl.r3;
-    const float2* tw;
-    TRY(fft_twiddles(c, pl.r3, &tw));
-    TRY(shared_table(c, n, R, F, M, peek, pl));
-    const int nseg = c->seg_count;
-    const int ncta = std::min(pl.ncta, nseg);
-    TRY(c->spec.ensure((size_t)bt.nf * nseg * 2 * L * sizeof(float2)));
-    TRY(c->partial.ensure((size_t)bt.nf * 2 * ncta * pl.HT * sizeof(float2)));
-    TRY(c->fftP.ensure((size_t)bt.nf * F * pl.HTP * sizeof(float2)));
-    {
-        fftc::LsSpecParams p{};
-        p.ref = ref; p.srv = srv; p.frame_stride = bt.stride;
-        p.n = (int)n; p.M = M; p.peek = peek; p.off = pl.off;
-        p.segs = c->seg_tab.as<fftc::Seg>(); p.nseg = nseg;
-        p.spec = c->spec.as<float2>(); p.partial = c->partial.as<float2>(); p.HT = pl.HT; p.tw = tw;
-        ProfScope ps(c, K_LAGCORR_LS);
-        PRC_R3_SWITCH(pl.r3, (fftc::lsspec_fft_kernel<R3><<<dim3(ncta, bt.nf), 16 * R3, fftc::lscorr_smem_float2<R3>() * sizeof(float2), c->stream>>>(p)));
-    }
-    TRY(check_launch("lsspec_fft_kernel"));
-    TRY(levinson_launch(c, ncta, pl.HT, M, reg, bt.nf));
-    TRY(c->wp_caf.ensure((size_t)bt.nf * L * sizeof(float2)));
-    {
-        fftc::TapSpec0Params p{};
-        p.taps = c->lstaps.as<float2>(); p.M = M; p.wp = c->wp_caf.as<float2>(); p.tw = tw;
-        ProfScope ps(c, K_MISC);
-        PRC_R3_SWITCH(pl.r3, (fftc::taps_spectrum0_kernel<R3><<<bt.nf, 16 * R3, fft_smem(R3), c->stream>>>(p)));
-    }
-    TRY(check_launch("taps_spectrum0_kernel"));
-    {
-        fftc::CafSpecParams p{};
-        p.ref = ref; p.frame_stride = bt.stride; p.win = win32; p.wp = c->wp_caf.as<float2>();
-        p.spec = c->spec.as<float2>(); p.segs = c->seg_tab.as<fftc::Seg>(); p.blk = c->seg_blk.as<int>();
-        p.nseg = nseg; p.n = (int)n; p.R = R; p.F = F; p.M = M;
-        p.P = c->fftP.as<float2>(); p.HT = pl.HTP; p.tw = tw;
-        ProfScope ps(c, K_LAGCORR_CAF);
-        PRC_R3_SWITCH(pl.r3, (fftc::cafspec_fft_kernel<R3><<<dim3(F, bt.nf), 16 * R3, fftc::caf_smem_float2<R3>() * sizeof(float2), c->stream>>>(p)));
-    }
-    TRY(check_launch("cafspec_fft_kernel"));
-    if (taps_out)
-        CU(cudaMemcpyAsync(taps_out, c->lstaps.p, (size_t)bt.nf * M * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
-    return doppler_stage(c, c->fftP.as<float2>(), 1, pl.HTP, pl.D + 1, 0, nullptr, nullptr, nullptr, pl.D, pl.c0, n, R, F, maps, bt);
-}
-
-// --------------------------------------------------------------------------- device pipelines
-// All pointers are device pointers; everything is enqueued on c->stream.
-
-
-// Doppler stage: P[j][lag] = sum of the partial rows (+ boundary sample), FFT along j, fftshift, column k = R - lag
-int doppler_stage(Ctx* c, const float2* src, int nchunk, int HT, long long ntaps, long long d_per_cta, const float2* bnd_x,
-                  const float2* bnd_s, const float* bnd_w, long long D, int c0, long long n, int R, int F, float2* out, Batch bt) {
-    if (c->tw_F != F) {
-        TRY(c->tw.ensure((size_t)F * sizeof(float2)));
-        twiddle_kernel<<<ceil_div(F, 256), 256, 0, c->stream>>>(c->tw.as<float2>(), F);
-        TRY(check_launch("twiddle_kernel"));
-        c->tw_F = F;
-    }
-    DopplerParams d{};
-    d.partial = src;
-    d.tw = c->tw.as<float2>();
-    d.out = out;
-    d.F = F; d.R = R; d.nchunk = nchunk; d.HT = HT;
-    d.partial_fstride = (long long)F * nchunk * HT;
-    d.out_fstride = (long long)F * (R + 1);
-    d.blk_len = (int)ntaps; d.per_cta = d_per_cta;
-    d.bx = bnd_x; d.bs = bnd_s; d.bwin = bnd_w; d.bstride = D; d.boff = c0; d.n = (int)n;
-    int logF = 0;
-    while ((1 << logF) < F) ++logF;
-    d.logF = logF;
-    const bool pow2 = (1 << logF) == F && F >= 2;
-    ProfScope ps_doppler(c, K_DOPPLER);
-    if (pow2 && F <= 8192) {
-        if (F <= 1024 && (long long)ceil_div(R + 1, 8) * bt.nf >= c->nsm) {
-            const size_t sm = (size_t)2 * F * 8 * sizeof(float2);
-            doppler_fft_pow2_kernel<8><<<dim3(ceil_div(R + 1, 8), bt.nf), 256, sm, c->stream>>>(d);
-        } else if (F <= 4096) {     // also the small-grid case: 2 columns per CTA fill more SMs
-            const size_t sm = (size_t)2 * F * 2 * sizeof(float2);
-            doppler_fft_pow2_kernel<2><<<dim3(ceil_div(R + 1, 2), bt.nf), 256, sm, c->stream>>>(d);
-        } else {
-            const size_t sm = (size_t)2 * F * sizeof(float2);
-            doppler_fft_pow2_kernel<1><<<dim3(R + 1, bt.nf), 256, sm, c->stream>>>(d);
-        }
-        TRY(check_launch("doppler_fft_pow2_kernel"));
-    } else {
-        TRY(c->pbuf.ensure((size_t)F * (R + 1) * sizeof(float2)));
-        for (int fr = 0; fr < bt.nf; ++fr) {      // any F: chunk sum + direct DFT, frame by frame
-            chunk_sum_kernel<<<ceil_div((long long)F * (R + 1), 256), 256, 0, c->stream>>>(
-                d.partial + (size_t)fr * d.partial_fstride, c->pbuf.as<float2>(), F, R, nchunk, HT, (int)ntaps, d_per_cta, d);
-            TRY(check_launch("chunk_sum_kernel"));
-            doppler_dft_kernel<<<dim3(ceil_div(R + 1, 128), F), 128, 0, c->stream>>>(
-                c->pbuf.as<float2>(), c->tw.as<float2>(), out + (size_t)fr * d.out_fstride, F, R);
-            TRY(check_launch("doppler_dft_kernel"));
-        }
-    }
-    return PRC_OK;
 }
 
 // bt.nf > 1 (a batch of frames) and fuse_wp != nullptr (clutter filter applied inside the CAF kernel, taps spectrum
@@ -1072,8 +879,51 @@ int xambg_device(Ctx* c, const float2* ref, const float2* srv, long long n, int 
     TRY(check_launch("lagcorr_kernel(caf)"));
     }
 
-    return doppler_stage(c, dop_src ? dop_src : c->partial.as<float2>(), g.nchunk, g.HT, ntaps, d_per_cta, bnd_x, srv, bnd_x ? bnd_w_all : nullptr,
-                         D, c0, n, R, F, out, bt);
+    // Doppler stage
+    if (c->tw_F != F) {
+        TRY(c->tw.ensure((size_t)F * sizeof(float2)));
+        twiddle_kernel<<<ceil_div(F, 256), 256, 0, c->stream>>>(c->tw.as<float2>(), F);
+        TRY(check_launch("twiddle_kernel"));
+        c->tw_F = F;
+    }
+    DopplerParams d{};
+    d.partial = dop_src ? dop_src : c->partial.as<float2>();
+    d.tw = c->tw.as<float2>();
+    d.out = out;
+    d.F = F; d.R = R; d.nchunk = g.nchunk; d.HT = g.HT;
+    d.partial_fstride = (long long)F * g.nchunk * g.HT;
+    d.out_fstride = (long long)F * (R + 1);
+    d.blk_len = (int)ntaps; d.per_cta = d_per_cta;
+    d.bx = bnd_x; d.bs = srv; d.bwin = bnd_x ? bnd_w_all : nullptr; d.bstride = D; d.boff = c0; d.n = (int)n;
+    int logF = 0;
+    while ((1 << logF) < F) ++logF;
+    d.logF = logF;
+    const bool pow2 = (1 << logF) == F && F >= 2;
+    ProfScope ps_doppler(c, K_DOPPLER);
+    if (pow2 && F <= 8192) {
+        if (F <= 1024 && (long long)ceil_div(R + 1, 8) * bt.nf >= c->nsm) {
+            const size_t sm = (size_t)2 * F * 8 * sizeof(float2);
+            doppler_fft_pow2_kernel<8><<<dim3(ceil_div(R + 1, 8), bt.nf), 256, sm, c->stream>>>(d);
+        } else if (F <= 4096) {     // also the small-grid case: 2 columns per CTA fill more SMs
+            const size_t sm = (size_t)2 * F * 2 * sizeof(float2);
+            doppler_fft_pow2_kernel<2><<<dim3(ceil_div(R + 1, 2), bt.nf), 256, sm, c->stream>>>(d);
+        } else {
+            const size_t sm = (size_t)2 * F * sizeof(float2);
+            doppler_fft_pow2_kernel<1><<<dim3(R + 1, bt.nf), 256, sm, c->stream>>>(d);
+        }
+        TRY(check_launch("doppler_fft_pow2_kernel"));
+    } else {
+        TRY(c->pbuf.ensure((size_t)F * (R + 1) * sizeof(float2)));
+        for (int fr = 0; fr < bt.nf; ++fr) {      // any F: chunk sum + direct DFT, frame by frame
+            chunk_sum_kernel<<<ceil_div((long long)F * (R + 1), 256), 256, 0, c->stream>>>(
+                d.partial + (size_t)fr * d.partial_fstride, c->pbuf.as<float2>(), F, R, g.nchunk, g.HT, (int)ntaps, d_per_cta, d);
+            TRY(check_launch("chunk_sum_kernel"));
+            doppler_dft_kernel<<<dim3(ceil_div(R + 1, 128), F), 128, 0, c->stream>>>(
+                c->pbuf.as<float2>(), c->tw.as<float2>(), out + (size_t)fr * d.out_fstride, F, R);
+            TRY(check_launch("doppler_dft_kernel"));
+        }
+    }
+    return PRC_OK;
 }
 
 // bt.nf > 1 (a batch of frames; taps_out then receives [nf][M]) and need_out == false (only the taps are wanted: the
@@ -1663,8 +1513,6 @@ int frame_device(Ctx* c, const float2* ref, const float2* srv, long long n, Batc
     const long long D = n / F;
     const LsFftPlan lf = (M >= 1 && M <= 2048) ? ls_fft_plan(c, n, M, bt.nf) : LsFftPlan{};
     const CafFftPlan cf = (D >= 2) ? caf_fft_plan(n, R, F, D + 1, D, true, M) : CafFftPlan{};
-    const SharedPlan sp = (lf.on && cf.on && !cleaned_out) ? shared_plan(c, n, R, F, M, peek, bt.nf) : SharedPlan{};
-    if (sp.on) return shared_frames(c, sp, ref, srv, n, bt, filter_len, peek, reg, R, F, win32, maps, taps_out);
     if (lf.on && cf.on) {
         // FFT-domain frame: lag sums -> Toeplitz solve -> taps spectrum -> CAF with the clutter filter applied to the
         // surveillance spectrum inside the kernel (the cleaned channel exists only if the caller asks for it)
@@ -2112,7 +1960,6 @@ int prc_set_option(const char* name, int value) {
     if (k == "fft") g_fft.store(value);
     else if (k == "fft_min_n") g_fft_min_n.store(value);
     else if (k == "caf_wave") g_caf_wave.store(value);
-    else if (k == "share") g_share.store(value);
     else return fail(PRC_E_INVALID, "unknown option '%s'", name);
     return PRC_OK;
 }
@@ -2124,7 +1971,6 @@ int prc_get_option(const char* name, int* value) {
     if (k == "fft") *value = g_fft.load();
     else if (k == "fft_min_n") *value = g_fft_min_n.load();
     else if (k == "caf_wave") *value = g_caf_wave.load();
-    else if (k == "share") *value = g_share.load();
     else return fail(PRC_E_INVALID, "unknown option '%s'", name);
     return PRC_OK;
 }

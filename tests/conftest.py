@@ -28,24 +28,20 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(params=["fft", "fft_noshare", "direct"])
+@pytest.fixture(params=["fft", "direct"])
 def both_paths(request):
-    """Run a GPU test on every shipped path (include/prcore.h: prc_set_option): "fft" = the FFT-domain kernels
-    (csrc/fftcorr.cuh, forced for every size they accept; fused frames share the windows' spectra between the LS and the
-    CAF kernel), "fft_noshare" = the same with separate LS / CAF kernels for fused frames, "direct" = the direct-form
-    kernels (tcgen05 / FP32).  Tests that compare against the separate operators treat both FFT variants alike."""
+    """Run a GPU test once on the FFT-domain kernels (csrc/fftcorr.cuh, forced for every size they accept) and once on
+    the direct-form kernels (tcgen05 / FP32): both are shipped and selectable (include/prcore.h: prc_set_option)."""
     from passiveradar_b200 import _lib
-    old = (_lib.get_option("fft"), _lib.get_option("fft_min_n"), _lib.get_option("share"))
-    if request.param.startswith("fft"):
+    old = (_lib.get_option("fft"), _lib.get_option("fft_min_n"))
+    if request.param == "fft":
         _lib.set_option("fft", 1)
         _lib.set_option("fft_min_n", 0)
-        _lib.set_option("share", 0 if request.param == "fft_noshare" else 1)
     else:
         _lib.set_option("fft", 0)
     yield request.param
     _lib.set_option("fft", old[0])
     _lib.set_option("fft_min_n", old[1])
-    _lib.set_option("share", old[2])
 
 
 def record_parity(name, **values):
