@@ -41,7 +41,7 @@ class FramePipeline:
     their copies and kernels."""
 
     def __init__(self, n, range_bins, freq_bins, filter_len=None, reg=1.0, peek=10,
-                 window=("kaiser", 5.0), device=None, nslots=3, batch=8):
+                 window=("kaiser", 5.0), device=None, nslots=4, batch=16):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.PrcoreError(_lib.PRC_E_CUDA, "FramePipeline needs a CUDA device (no CPU fallback)")

@@ -10,7 +10,7 @@ import torch
 from passiveradar_b200 import _lib, synth
 from passiveradar_b200.frames import FramePipeline
 
-n, F, R, B = 2 ** 20, 256, 300, 64
+n, F, R, B = 2 ** 20, 256, 300, 125
 dev = torch.device("cuda", 0)
 fr = [synth.make_frame(n, "P1", i) for i in range(4)]
 ref_d = torch.from_numpy(np.stack([fr[i % 4][0] for i in range(B)])).to(dev)
@@ -20,7 +20,7 @@ if len(sys.argv) > 1:
     for kv in sys.argv[1:]:
         k, v = kv.split("=")
         _lib.set_option(k, int(v))
-for batch, slots in ((16, 3), (16, 1)):
+for batch, slots in ((16, 3), (25, 3), (25, 2), (32, 2), (32, 3), (42, 3), (63, 2), (16, 4), (25, 5)):
     pipe = FramePipeline(n, R, F, batch=batch, nslots=slots)
     for _ in range(3):
         pipe.run_device(ref_d, srv_d, maps)
