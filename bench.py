@@ -678,7 +678,8 @@ def run_sweep(args, rank, world, local_rank):
         for F in SWEEP_F:
             cfg = dict(n=n, F=F, R=300, filter_len=300, peek=10, reg=1.0, clutter="ls", name=f"sweep n={n} F={F} R=300")
             a = argparse.Namespace(**vars(args))
-            a.resident = max(16, min(125, (2 ** 31) // (16 * n)))
+            a.resident = max(20, min(125, (2 ** 31) // (16 * n))) // 5 * 5
+            a.batch = a.resident // 5                      # five even calls per pass, one per slot
             a.steps = min(base_steps, 5)
             a.frames_per_step = max(a.resident, int(8000 * 2 ** 20 / n / a.steps))      # ~0.3 s of GPU time per point
             a.no_cpu_baseline = True
