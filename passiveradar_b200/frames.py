@@ -106,6 +106,10 @@ class FramePipeline:
         stride = ref_d.stride(0) if nf > 1 else self.n
         if nf > 1 and srv_d.stride(0) != stride:
             raise ValueError("ref_d and srv_d must have the same frame stride")
+        if ref_d.stride(-1) != 1 or srv_d.stride(-1) != 1 or not maps_d.is_contiguous():
+            raise ValueError("frames must be contiguous along the sample axis and maps_d must be contiguous")
+        if maps_d.shape[0] < nf or tuple(maps_d.shape[1:3]) != (self.F, self.R + 1):
+            raise ValueError(f"maps_d must have shape (>= {nf}, {self.F}, {self.R + 1})")
         cur = torch.cuda.current_stream(self.tdev)
         fork = torch.cuda.Event()
         fork.record(cur)
