@@ -428,7 +428,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
 
     n, F, R = cfg["n"], cfg["F"], cfg["R"]
     nlms = cfg["clutter"] == "nlms"
-    resident = args.resident or (296 if nlms else 125)
+    resident = args.resident or (444 if nlms else 125)
     fps_guess = 450.0 if nlms else 25000.0
     frames_per_step = args.frames_per_step or (resident if nlms else 4000)
     work = Workload(args, cfg, torch, dev, local_rank)
@@ -474,7 +474,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
     # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
     nb_host = ref_base.shape[0]
     if nlms:
-        nb_host = 74                 # NLMS runs one CTA per frame: a call must carry enough frames to use the GPU
+        nb_host = 148                # NLMS runs one CTA per frame: a call must carry enough frames to use the GPU
     ref_h = pinned_empty((nb_host, n))
     srv_h = pinned_empty((nb_host, n))
     for i in range(nb_host):
@@ -485,7 +485,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
     if nlms:
         stage = (torch.empty((nb_host, n), dtype=torch.complex64, device=dev), torch.empty((nb_host, n), dtype=torch.complex64, device=dev),
                  torch.empty((nb_host, F, R + 1), dtype=torch.complex64, device=dev))
-    e2e_frames_per_step = max(nb_host, int(round((74 if nlms else 640) / nb_host)) * nb_host)
+    e2e_frames_per_step = max(nb_host, int(round((148 if nlms else 640) / nb_host)) * nb_host)
     passes = e2e_frames_per_step // nb_host
     for _ in range(2):
         work.run_host(ref_h, srv_h, maps_h, stage)

@@ -31,8 +31,12 @@ constexpr int NB_PAD = 64;           // extra reference samples staged behind a 
 //   P1    [32][NB_L]                 per-warp partial dot products
 //   Gs    [NB_L][NB_L + 1]           g(m, m + delta)
 //   es    [NB_L]                     mu conj(e_l) / p_l ;  invp [NB_L] floats (mu / p_m)
-template <int KT>
-__global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_constant__ NlmsParams pg) {
+// NT threads (1024: lowest latency of one frame; 512: two CTAs fit on an SM, for batches of independent frames):
+// NT / 32 warps share the 32 Gram lags and the tap segments, KT * NT >= M taps are owned by the threads
+template <int KT, int NT = NB_THREADS>
+__global__ void __launch_bounds__(NT, NT == 512 ? 3 : 1) nlms_block_kernel(const __grid_constant__ NlmsParams pg) {
+    constexpr int NB_THREADS = NT;
+    constexpr int NWARP = NT / 32;
     extern __shared__ __align__(16) float2 nbs[];
     const NlmsParams p = nlms_frame_params(pg);
     const int M = p.filter_len + p.peek;
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_con
 #pragma unroll
     for (int r = 0; r < KT; ++r) grad[r] = make_float2(0.f, 0.f);
     int in_block = 0;
-    const int S = (M + 31) / 32;                      // taps per warp in the dot-product phase
+    const int S = (M + NWARP - 1) / NWARP;            // taps per warp in the dot-product phase
     const long long nref = p.n;
 
     for (int ts = 0; ts < nsteps; ts += NLMS_TILE) {
@@ -94,9 +98,8 @@ __global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_con
                 }
                 P1[warp * NB_L + lane] = make_float2(ar, ai);
             }
-            // ---- phase A2: Gram lag delta = warp: g(m, m + delta), m = lane
-            {
-                const int delta = warp;
+            // ---- phase A2: Gram lags delta = warp, warp + NWARP, ...: g(m, m + delta), m = lane
+            for (int delta = warp; delta < 32; delta += NWARP) {
                 const float2* t0 = tile + kk0;
                 float cr = 0.f, ci = 0.f;
                 for (int q = lane; q < M; q += 32) {                      // direct sum for m = 0
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(NB_THREADS) nlms_block_kernel(const __grid_con
             if (warp == 0) {
                 float sr = 0.f, si = 0.f;
 #pragma unroll 8
-                for (int q = 0; q < 32; ++q) {
+                for (int q = 0; q < NWARP; ++q) {
                     const float2 v = P1[q * NB_L + lane];
                     sr += v.x; si += v.y;
                 }

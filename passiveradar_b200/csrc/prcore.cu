@@ -253,6 +253,9 @@ int set_kernel_attrs(int device) {
     CU(cudaFuncSetAttribute(nlms_block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(nlms_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     CU(cudaFuncSetAttribute(nlms_block_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_block_kernel<1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_block_kernel<2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    CU(cudaFuncSetAttribute(nlms_block_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
 #define PRC_FFT_ATTRS(R3)                                                                                              \
     CU(cudaFuncSetAttribute(fftc::lscorr_fft_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));           \
     CU(cudaFuncSetAttribute(fftc::taps_spectrum_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));        \
@@ -1385,6 +1388,13 @@ int nlms_device(Ctx* c, const float2* ref, const float2* srv, long long n, int f
         // exact evaluation 32 samples at a time (nlms_block.cuh), 4x the speed of the sample-serial kernel at
         // config 4; block_len > 1 (block_NLMS) freezes the taps inside a user block
         const size_t sb = nlms_block_smem(M);
+        if (bt.nf > c->nsm && M <= 2048) {
+            // more frames than SMs: 512-thread CTAs, two resident per SM (a 1024-thread CTA owns the SM's registers)
+            if (M <= 512) nlms_block_kernel<1, 512><<<bt.nf, 512, sb, c->stream>>>(p);
+            else if (M <= 1024) nlms_block_kernel<2, 512><<<bt.nf, 512, sb, c->stream>>>(p);
+            else nlms_block_kernel<4, 512><<<bt.nf, 512, sb, c->stream>>>(p);
+            return check_launch("nlms_block_kernel");
+        }
         if (kt == 1) nlms_block_kernel<1><<<bt.nf, NB_THREADS, sb, c->stream>>>(p);
         else if (kt == 2) nlms_block_kernel<2><<<bt.nf, NB_THREADS, sb, c->stream>>>(p);
         else nlms_block_kernel<4><<<bt.nf, NB_THREADS, sb, c->stream>>>(p);
