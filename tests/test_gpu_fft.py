@@ -295,3 +295,34 @@ def test_stream_frames_over_nccl_world2():
         assert p.exitcode == 0
     for rank, ok, worst in res:
         assert ok and worst <= 2e-6, (rank, ok, worst)
+
+
+def test_nlms_large_batch_uses_the_half_size_ctas_and_matches():
+    """More frames than SMs: prc_nlms_frames_c64 switches to 512-thread CTAs (three per SM).  Same recurrence, another
+    summation order of the partial dot products: compare with the single-frame kernel and with the reference-pinned C oracle."""
+    import torch
+    from oracle import clutter_oracle as co
+    props = torch.cuda.get_device_properties(0)
+    nf = props.multi_processor_count + 12
+    n, fl, peek, mu = 2 ** 13, 400, 10, 0.05
+    base = [synth.make_frame(n, "P1", frame=80 + i) for i in range(4)]
+    dev = torch.device("cuda", 0)
+    ref_d = torch.from_numpy(np.stack([base[i % 4][0] for i in range(nf)])).to(dev)
+    srv_d = torch.from_numpy(np.stack([base[i % 4][1] for i in range(nf)])).to(dev)
+    out = torch.empty((nf, n), dtype=torch.complex64, device=dev)
+    taps = torch.empty((nf, fl + peek), dtype=torch.complex64, device=dev)
+    lib = _lib.load()
+    st = torch.cuda.Stream(device=dev)
+    _lib.check(lib.prc_nlms_frames_c64(ref_d.data_ptr(), srv_d.data_ptr(), n, nf, n, fl, peek, mu, 1, None, out.data_ptr(),
+                                       taps.data_ptr(), _lib.MEM_DEVICE, 0, st.cuda_stream, 0))
+    got = out.cpu().numpy()
+    gt = taps.cpu().numpy()
+    for i in (0, 1, 2, 3, nf - 1):
+        ref, srv = base[i % 4]
+        want, ww = co.block_nlms_oracle_c(ref, srv, fl, mu, peek, 1)
+        single, st1 = prb.NLMS_filter(ref, srv, fl, mu, peek, None, True)
+        den = float(np.abs(want).max())
+        assert G.rel_inf(got[i], want, den=den) <= TOL
+        assert G.rel_inf(got[i], single, den=den) <= 2e-6
+        assert G.rel_inf(gt[i], st1) <= 5e-5
+    assert np.array_equal(got[0], got[4])          # same frame on another CTA: deterministic
