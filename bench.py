@@ -217,6 +217,42 @@ def _cpu_sample_worker(job):
     return t_f * div + t_x * (R + 1) / (Rs + 1), t_f, t_x
 
 
+def cpu_full_frame(cfg, profile, timeout=240):
+    """ONE whole frame through the reference's own functions in one process with all BLAS threads: nothing sampled,
+    nothing extrapolated.  It checks the scaling of the pool's bounded sample (one frame takes about a minute and 8 GB,
+    which is why the pool does not do this in every worker).  Returns a dict or None."""
+    code = (
+        "import json, sys, time, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "import scipy.signal as signal\n"
+        "from passiveradar_b200 import synth\n"
+        f"cfg = {cfg!r}\n"
+        "LS_Filter, NLMS_filter, fast_xambg, kind = bench._ref_modules()\n"
+        "bench._install_decimate_shim()\n"
+        f"ref, srv = synth.make_frame(cfg['n'], {profile!r}, 999)\n"
+        "w = signal.get_window(('kaiser', 5.0), cfg['n'])\n"
+        "t0 = time.perf_counter()\n"
+        "clean = LS_Filter(ref, srv, cfg['filter_len'], cfg['reg'], cfg['peek'])\n"
+        "t1 = time.perf_counter()\n"
+        "fast_xambg(ref, clean, cfg['R'], cfg['F'], cfg['n'], w)\n"
+        "t2 = time.perf_counter()\n"
+        "print(json.dumps({'ls_seconds': t1 - t0, 'xambg_seconds': t2 - t1, 'kind': kind}))\n")
+    env = dict(os.environ)
+    for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout, env=env)
+        if res.returncode != 0:
+            return None
+        out = json.loads(res.stdout.strip().splitlines()[-1])
+        out["frames_per_s_one_process"] = 1.0 / (out["ls_seconds"] + out["xambg_seconds"])
+        out["note"] = "one whole frame, LS_Filter -> fast_xambg, one process, default BLAS threads, no sampling"
+        return out
+    except Exception:
+        return None
+
+
 class CpuArm:
     """Frame-parallel pool, one process per host core (1 BLAS thread each), as SURVEY 8d asks."""
 
@@ -631,6 +667,8 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
                    "filter_extrapolated": arm.div > 1, "wall_s": wall}
         finally:
             arm.close()
+        if cfg["clutter"] == "ls":
+            cpu["full_frame_check"] = cpu_full_frame(cfg, args.profile)
 
     line = None
     if rank == 0:
