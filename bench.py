@@ -256,7 +256,7 @@ def cpu_full_frame(cfg, profile, timeout=240):
 class CpuArm:
     """Frame-parallel pool, one process per host core (1 BLAS thread each), as SURVEY 8d asks."""
 
-    def __init__(self, cfg, procs, profile, nlms_block=1, bounded=False):
+    def __init__(self, cfg, procs, profile, nlms_block=1, bounded=False, blas_threads=0):
         """bounded=False: the sample of `cpu_baseline` (one round: fast_xambg on the whole frame, every lag measured).
         bounded=True: the reference arm's step, repeated steps + warmup times, so a step is cut to a few seconds
         (fast_xambg on 1/8 of the range lags, clutter filter on a shorter piece)."""
@@ -282,9 +282,13 @@ class CpuArm:
             mem_gb = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
         except (ValueError, OSError):
             mem_gb = 16
-        self.procs = procs if procs > 0 else max(1, min(ncpu, int(mem_gb // 3), 64))
+        # measured on the GPU box's host (128 logical CPUs, profiles/r02_cpu_pool.log): the workers are memory-bandwidth
+        # bound; 32 workers x 4 BLAS threads give the best whole-pool rate (0.51 frames/s; 64 x 2: 0.47, 16 x 8: 0.44,
+        # 8 x 16: 0.27), so the arm uses one worker per four logical CPUs
+        self.procs = procs if procs > 0 else max(1, min(ncpu // 4 if ncpu >= 8 else ncpu, int(mem_gb // 3), 64))
+        self.blas_threads = blas_threads if blas_threads > 0 else max(1, ncpu // self.procs)
         for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
-            os.environ[k] = "1"
+            os.environ[k] = str(self.blas_threads)
         self.kind = _ref_modules()[3]
         self.pool = mp.get_context("spawn").Pool(self.procs)
         self.round = 0
@@ -314,7 +318,7 @@ class CpuArm:
         lags = (f"all {c['R'] + 1} range lags (measured" if self.lag_div == 1 else
                 f"{(c['R'] + 1) // self.lag_div} of {c['R'] + 1} range lags, time x{(c['R'] + 1) / ((c['R'] + 1) // self.lag_div):.2f} (EXTRAPOLATED: every lag costs the same")
         return (f"per worker, {src}: {ext} + fast_xambg on the FULL {c['n']}-sample frame, {lags}; scipy.signal.decimate's np.roots "
-                f"detour bypassed bit-identically); {self.procs} workers in parallel, 1 BLAS thread each")
+                f"detour bypassed bit-identically); {self.procs} workers in parallel, {self.blas_threads} BLAS thread(s) each")
 
     def close(self):
         self.pool.terminate()
