@@ -345,7 +345,7 @@ def run_reference(args, cfg, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (f32 pairs; f64 block sums)",
         "data": "synthetic", "config": config_dict(cfg, args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs, "kind": arm.kind,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.procs * arm.blas_threads, "workers": arm.procs, "kind": arm.kind,
                          "sample": arm.sample_text(), "filter_extrapolated": arm.div > 1, "xambg_extrapolated": arm.lag_div > 1},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -666,7 +666,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
         arm = CpuArm(cfg, args.cpu_procs, args.profile, args.nlms_block)
         try:
             fps, wall, est, t_f, t_x = arm.step()
-            cpu = {"value": fps, "unit": UNIT, "cores": arm.procs, "kind": arm.kind, "sample": arm.sample_text(),
+            cpu = {"value": fps, "unit": UNIT, "cores": arm.procs * arm.blas_threads, "workers": arm.procs, "kind": arm.kind, "sample": arm.sample_text(),
                    "est_seconds_per_frame_per_core": est, "filter_seconds_sampled": t_f, "xambg_seconds_full_frame": t_x,
                    "filter_extrapolated": arm.div > 1, "wall_s": wall}
         finally:
