@@ -44,6 +44,11 @@ CONFIGS = {
     "c4": dict(n=2 ** 21, F=512, R=400, filter_len=400, peek=10, mu=0.05, clutter="nlms",
                name="2M-sample CPI (2^21), 512 Doppler x 400 range, NLMS_filter(filterLen=400, mu=0.05, peek=10) -> fast_xambg(kaiser 5.0)"),
 }
+# not a BASELINE config: the chunk main.py really processes with the shipped PRconfig.yaml (config.py:13-59 -> N = 524 288,
+# F = 1024, R = 175; clutter filter main.py:169-176 = LS_Filter_Multiple over five Doppler bins at the IF rate)
+CONFIGS["main"] = dict(n=524288, F=1024, R=175, filter_len=175, peek=10, clutter="multi", bins=[0.0, 1.0, -1.0, 2.0, -2.0],
+                       fs=2.4e6 * 13 / 119,
+                       name="PRconfig.yaml chunk: 524288-sample CPI, 1024 Doppler x 175 range, LS_Filter_Multiple(175, [0,1,-1,2,-2]) -> fast_xambg(kaiser 5.0)")
 SWEEP_N = [2 ** 18, 2 ** 19, 2 ** 20, 2 ** 21, 2 ** 22]
 SWEEP_F = [64, 256, 1024]
 METRIC = "CPI frames/sec (1M-sample CPI, 256 Doppler x 300 range)"
@@ -72,7 +77,7 @@ def parse_args():
 def config_dict(cfg, args, world):
     """The `config` object of the JSON line -- identical on both arms."""
     return {"workload": cfg["name"], "profile": args.profile, "n": cfg["n"], "doppler_bins": cfg["F"], "range_bins": cfg["R"],
-            "clutter_filter": "LS_Filter" if cfg["clutter"] == "ls" else ("NLMS_filter" if args.nlms_block == 1 else f"block_NLMS(blockLen={args.nlms_block})"),
+            "clutter_filter": {"ls": "LS_Filter", "multi": "LS_Filter_Multiple"}.get(cfg["clutter"]) or ("NLMS_filter" if args.nlms_block == 1 else f"block_NLMS(blockLen={args.nlms_block})"),
             "parallelism": f"frames sharded over {world} GPU(s), no collective on the data path"}
 
 
@@ -86,10 +91,11 @@ def kernel_alg_bytes(cfg):
     """Algorithmic bytes per FRAME for each kernel of the frame."""
     n, F, R = cfg["n"], cfg["F"], cfg["R"]
     M = cfg["filter_len"] + cfg["peek"]
+    nb = len(cfg.get("bins", [0]))
     return {
-        "lagcorr_ls": 2 * 8 * n + 2 * 8 * M,        # read ref, srv; write 2 x M correlation lags
+        "lagcorr_ls": nb * (2 * 8 * n + 2 * 8 * M), # read ref, srv; write 2 x M correlation lags (per Doppler bin of LS_Filter_Multiple)
         "levinson": 2 * 8 * M + 8 * M,
-        "fir_apply": 3 * 8 * n,                     # read ref, srv; write cleaned srv
+        "fir_apply": nb * 3 * 8 * n,                # read ref, srv; write cleaned srv
         "lagcorr_caf": 2 * 8 * n + 4 * n + 8 * F * (R + 1),   # ref, srv, f32 window; block sums
         "doppler_fft": 2 * 8 * F * (R + 1),
         "nlms": 3 * 8 * n,
@@ -161,11 +167,13 @@ def _ref_modules():
     if os.path.isdir(os.path.join(ref_dir, "passiveRadar")):
         if ref_dir not in sys.path:
             sys.path.insert(0, ref_dir)
-        from passiveRadar.clutter_removal import LS_Filter, NLMS_filter
+        from passiveRadar.clutter_removal import LS_Filter, NLMS_filter, LS_Filter_Multiple
         from passiveRadar.range_doppler_processing import fast_xambg
+        _ref_modules.multi = LS_Filter_Multiple
         return LS_Filter, NLMS_filter, fast_xambg, "reference"
     from oracle import clutter_oracle as co
     from oracle import xambg_oracle as xo
+    _ref_modules.multi = co.ls_filter_multiple_oracle
     return co.ls_filter_oracle, co.nlms_filter_oracle, xo.fast_xambg_oracle, "port"
 
 
@@ -207,6 +215,8 @@ def _cpu_sample_worker(job):
     t0 = time.perf_counter()
     if cfg["clutter"] == "ls":
         LS_Filter(ref[:ns], srv[:ns], cfg["filter_len"], cfg["reg"], cfg["peek"])
+    elif cfg["clutter"] == "multi":
+        _ref_modules.multi(ref[:ns], srv[:ns], cfg["filter_len"], cfg["fs"], cfg["bins"])
     else:
         NLMS_filter(ref[:ns], srv[:ns], cfg["filter_len"], cfg["mu"], cfg["peek"])
     t_f = time.perf_counter() - t0
@@ -273,7 +283,7 @@ class CpuArm:
         # bounded sample: LS_Filter at full size builds a 2.6 GB data matrix twice over (33-62 s, 8 GB RSS per frame);
         # n/8 keeps a worker at ~1 GB and a few seconds.  NLMS_filter is a Python loop of 8.8 us per sample: n/32.
         big = cfg["n"] >= 2 ** 19
-        self.div = (8 if cfg["clutter"] == "ls" else 32) if big else 1
+        self.div = {"ls": 8, "multi": 1}.get(cfg["clutter"], 32) if big else 1      # LS_Filter_Multiple: Toeplitz filters, whole frame measured
         self.lag_div = 1
         if bounded and big:
             self.div *= 4
@@ -311,7 +321,7 @@ class CpuArm:
 
     def sample_text(self):
         c = self.cfg
-        flt = "LS_Filter" if c["clutter"] == "ls" else "NLMS_filter"
+        flt = {"ls": "LS_Filter", "multi": "LS_Filter_Multiple"}.get(c["clutter"], "NLMS_filter")
         src = "the reference's own functions (baseline/_ref, unmodified)" if self.kind == "reference" else "the oracle port"
         ext = (f"{flt} on n/{self.div} = {c['n'] // self.div} samples with all {c['filter_len'] + c['peek']} taps, time x{self.div} "
                f"(EXTRAPOLATED: cost linear in n)") if self.div > 1 else f"{flt} on the full frame"
@@ -401,6 +411,7 @@ class Workload:
         n, F, R = cfg["n"], cfg["F"], cfg["R"]
         self.n, self.F, self.R = n, F, R
         self.local_rank = local_rank
+        self.bins = np.ascontiguousarray(cfg.get("bins", [0.0]), dtype=np.float64)
         if cfg["clutter"] == "ls":
             self.pipe = FramePipeline(n, R, F, filter_len=cfg["filter_len"], reg=cfg["reg"], peek=cfg["peek"],
                                       window=("kaiser", 5.0), device=local_rank, nslots=args.slots, batch=args.batch)
@@ -422,6 +433,16 @@ class Workload:
         self.stream.wait_stream(cur)
         st = self.stream.cuda_stream
         flags = _lib.FLAG_ASYNC | _lib.FLAG_WINDOW_F32
+        if c["clutter"] == "multi":
+            stride = ref_d.stride(0) if nf > 1 else self.n
+            assert stride == self.n, "bench frames are contiguous"
+            _lib.check(self.lib.prc_ls_multiple_frames_c64(ref_d.data_ptr(), srv_d.data_ptr(), self.n, nf, stride, c["filter_len"], c["peek"],
+                                                           c["fs"], self.bins.ctypes.data, len(self.bins), self.clean.data_ptr(),
+                                                           _lib.MEM_DEVICE, self.local_rank, st, _lib.FLAG_ASYNC))
+            _lib.check(self.lib.prc_xambg_frames_c64(ref_d.data_ptr(), self.clean.data_ptr(), self.n, nf, stride, self.R, self.F,
+                                                     self.window.data_ptr(), maps_d.data_ptr(), _lib.MEM_DEVICE, self.local_rank, st, flags))
+            cur.wait_stream(self.stream)
+            return
         _lib.check(self.lib.prc_nlms_frames_c64(ref_d.data_ptr(), srv_d.data_ptr(), self.n, nf, ref_d.stride(0) if nf > 1 else self.n,
                                                 c["filter_len"], c["peek"], c["mu"], self.args.nlms_block, None,
                                                 self.clean.data_ptr(), None, _lib.MEM_DEVICE, self.local_rank, st, _lib.FLAG_ASYNC))
@@ -468,6 +489,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
 
     n, F, R = cfg["n"], cfg["F"], cfg["R"]
     nlms = cfg["clutter"] == "nlms"
+    direct = cfg["clutter"] != "ls"          # clutter filter and CAF as two batched library calls (no FramePipeline)
     resident = args.resident or (444 if nlms else 125)
     fps_guess = 450.0 if nlms else 25000.0
     frames_per_step = args.frames_per_step or (resident if nlms else 4000)
@@ -522,7 +544,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
         srv_h[i] = srv_base[i % srv_base.shape[0]]
     maps_h = pinned_empty((nb_host, F, R + 1, 1))
     stage = None
-    if nlms:
+    if direct:
         stage = (torch.empty((nb_host, n), dtype=torch.complex64, device=dev), torch.empty((nb_host, n), dtype=torch.complex64, device=dev),
                  torch.empty((nb_host, F, R + 1), dtype=torch.complex64, device=dev))
     e2e_frames_per_step = max(nb_host, int(round((148 if nlms else 640) / nb_host)) * nb_host)
@@ -542,7 +564,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
     # ---- the reference's own call signatures from a thread pool (main.py:169-194 under dask's threaded scheduler):
     # pageable numpy arrays in, numpy arrays out, one library workspace per calling thread
     dropin = None
-    if rank == 0 and not nlms and not quiet:
+    if rank == 0 and not direct and not quiet:
         import concurrent.futures as cf
         import scipy.signal as signal
         import passiveradar_b200 as prb
@@ -639,7 +661,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
                     "peak_source": peaks["source"] + ", " + peaks["of"],
                     "path": "fft" if _lib.get_option("fft") else "direct (tcgen05 / FP32)"}
         # single-frame latency: one frame, one stream, synchronised
-        if not nlms:
+        if not direct:
             lat = Workload(args1, cfg, torch, dev, local_rank)
             lat.pipe.batch = 1
             for _ in range(3):
@@ -655,7 +677,7 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
 
     # ---- config 3: the 1000-frame stream held by rank 0, staged over NCCL, double buffered against compute
     stream = None
-    if world > 1 and not args.no_stream and not nlms:
+    if world > 1 and not args.no_stream and not direct:
         from passiveradar_b200 import distributed as pd
         stream = pd.stream_benchmark(work.pipe, ref_d, srv_d, maps_d, nframes_total=1000, chunk=args.batch, rank=rank, world=world,
                                      device=dev)
@@ -681,14 +703,15 @@ def run_b200(args, cfg, rank, world, local_rank, quiet=False):
             "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "c64 (f32 pairs: FP32 FFT-domain block correlations; f64 Toeplitz solve)" if not nlms else "c64 (f32 pairs)",
+            "metric_note": None if args.config in ("c2", "c3") else f"frames/s of config {args.config!r}, not of the headline configuration",
             "data": "synthetic", "config": config_dict(cfg, args, world),
             "run": {"frames_per_step_per_gpu": frames_per_step, "resident_distinct_frames_per_gpu": resident,
                     "frames_per_call": args.batch, "slots": args.slots, "timed_region_s": round(ms * 1e-3, 3),
                     "cache": f"resident set {resident * 2 * n * 8 / 2 ** 20:.0f} MiB per GPU > 126 MB L2 (no flush needed)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_frames_per_step * 2 * n * 8,
                     "d2h_bytes_per_step": e2e_frames_per_step * F * (R + 1) * 8, "frames_per_step_per_gpu": e2e_frames_per_step,
-                    "api": "passiveradar_b200.frames.FramePipeline.run_host (pinned host ndarrays)" if not nlms else
-                           "prc_nlms_frames_c64 + prc_xambg_frames_c64 around pinned host ndarrays",
+                    "api": "passiveradar_b200.frames.FramePipeline.run_host (pinned host ndarrays)" if not direct else
+                           "clutter-filter + prc_xambg_frames_c64 batched calls around pinned host ndarrays",
                     "h2d_GBps": round(e2e_frames_per_step * 2 * n * 8 * args.steps / e2e_s / 1e9, 2),
                     "h2d_link_GBps": round(h2d_peak, 2) if h2d_peak else None,
                     "note": "h2d_GBps = input bytes per second per GPU through the timed region; h2d_link_GBps = plain "

@@ -125,6 +125,14 @@ int prc_ls_multiple_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int f
                         prc_c64* out, prc_c64* taps_last,
                         int mem_kind, int device, void* stream, unsigned flags);
 
+/* prc_ls_multiple_frames_c64: LS_Filter_Multiple on nframes independent chunks per call (device pointers; frame i at
+ * ref/srv/out + i*frame_stride): what main.py:169-176 does per dask chunk, several chunks at a time.  One launch of each
+ * kernel per Doppler bin covers the batch.
+ */
+int prc_ls_multiple_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                               int filter_len, int peek, double sample_rate, const double* doppler_bins, int nbins,
+                               prc_c64* out, int mem_kind, int device, void* stream, unsigned flags);
+
 /* ---- NLMS / block-NLMS clutter filter ---------------------------------------------------
  * Replaces NLMS_filter(), reference passiveRadar/clutter_removal.py:189-249
  * (block_len == 1) and provides block_NLMS (block_len > 1; not in the reference,

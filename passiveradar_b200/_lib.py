@@ -56,6 +56,8 @@ SIGNATURES = {
                                       C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_ls_multiple_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int,
                                       _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "prc_ls_multiple_frames_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                             C.c_int, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_nlms_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, _c64p,
                                _c64p, _c64p, C.c_int, C.c_int, C.c_void_p, C.c_uint]),
     "prc_frame_c64": (C.c_int, [_c64p, _c64p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,

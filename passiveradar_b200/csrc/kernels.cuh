@@ -818,9 +818,11 @@ __global__ void doppler_dft_kernel(const float2* __restrict__ P, const float2* _
 // np.roll(frequency_shift(ref, fc, Fs), -peek) with the reference's float32 phase ramp
 // (signal_utils.py:24-27: arange(..., dtype=complex64)); shift == 0 is a plain roll.
 __global__ void shift_roll_kernel(const float2* __restrict__ ref, float2* __restrict__ rs, int n, int peek,
-                                  int shift, float B, float rFs) {
+                                  int shift, float B, float rFs, long long frame_stride = 0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    ref += (size_t)blockIdx.y * frame_stride;          // a batch of frames in blockIdx.y
+    rs += (size_t)blockIdx.y * frame_stride;
     int j = i + peek;
     if (j >= n) j %= n;
     float2 v = ref[j];

@@ -643,7 +643,8 @@ int fir_fft(Ctx* c, int r3, const float2* ref, const float2* srv, float2* out, l
     p.n = (int)n; p.M = M; p.peek = peek; p.linear = linear ? 1 : 0;
     p.nseg = ceil_div(n, L - M + 1);
     p.tw = tw;
-    const int per_frame = std::max(1, std::min(p.nseg, ceil_div(4 * c->nsm, bt.nf)));
+    // one wave of CTAs for the whole batch (3 resident per SM: 68 KB of shared memory each)
+    const int per_frame = (int)std::max<long long>(1, std::min<long long>(p.nseg, 3ll * c->nsm / bt.nf));
     {
         ProfScope ps(c, K_FIR);
         PRC_R3_SWITCH(r3, (fftc::fir_fft_kernel<R3><<<dim3(per_frame, bt.nf), 16 * R3, fftc::fir_smem_float2<R3>() * sizeof(float2), c->stream>>>(p)));
@@ -1193,20 +1194,23 @@ int ls_device(Ctx* c, const float2* ref, const float2* srv, long long n, int fil
 // LS_Filter_Toeplitz (reference clutter_removal.py:109-160) on the device: roll (and optionally
 // frequency-shift) the reference, then the LS pipeline in linear mode with reg = 0 and all
 // filterLen + peek taps causal on the rolled reference.
+// bt.nf > 1: a batch of frames, every buffer (ref, srv, out, the rolled reference) bt.stride samples apart (FFT-domain path)
 int ls_toeplitz_device(Ctx* c, const float2* ref, const float2* srv, long long n, int filter_len, int peek,
-                       bool shift, double fc, double fs, float2* out, float2* taps_out) {
+                       bool shift, double fc, double fs, float2* out, float2* taps_out, Batch bt = Batch{}) {
     if (n <= 0 || n >= (1ll << 31) - 4096) return fail(PRC_E_INVALID, "n=%lld unsupported", n);
     if (filter_len < 0 || peek < 0 || filter_len + peek < 1)
         return fail(PRC_E_INVALID, "filter_len=%d peek=%d invalid", filter_len, peek);
-    TRY(c->rs.ensure((size_t)n * sizeof(float2)));
+    const long long stride = bt.nf > 1 ? bt.stride : n;
+    TRY(c->rs.ensure(((size_t)(bt.nf - 1) * stride + n) * sizeof(float2)));
     // complex64(1j*2*pi*fc) * complex64(n) / Fs, evaluated like numpy does (see shift_roll_kernel)
     const float B = (float)(2.0 * 3.14159265358979323846 * fc);
     {
         ProfScope ps(c, K_MISC);
-        shift_roll_kernel<<<ceil_div(n, 256), 256, 0, c->stream>>>(ref, c->rs.as<float2>(), (int)n, peek, shift ? 1 : 0, B, 1.0f / (float)fs);
+        shift_roll_kernel<<<dim3(ceil_div(n, 256), bt.nf), 256, 0, c->stream>>>(ref, c->rs.as<float2>(), (int)n, peek, shift ? 1 : 0, B,
+                                                                                 1.0f / (float)fs, stride);
     }
     TRY(check_launch("shift_roll_kernel"));
-    return ls_device(c, c->rs.as<float2>(), srv, n, filter_len + peek, 0, 0.0, out, taps_out, nullptr, nullptr, nullptr, true);
+    return ls_device(c, c->rs.as<float2>(), srv, n, filter_len + peek, 0, 0.0, out, taps_out, nullptr, nullptr, nullptr, true, bt);
 }
 
 // ---- front end (frontend.cuh) -------------------------------------------------------------------
@@ -2033,6 +2037,39 @@ int prc_ls_multiple_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int f
     if (mem_kind == PRC_MEM_HOST) {
         TRY(d2h(c, out, cur, nb, flags));
         if (taps_last) TRY(d2h(c, taps_last, c->lstaps.p, (size_t)M * sizeof(float2), flags));
+    }
+    return finish(c, flags);
+}
+
+int prc_ls_multiple_frames_c64(const prc_c64* ref, const prc_c64* srv, int64_t n, int nframes, int64_t frame_stride,
+                               int filter_len, int peek, double sample_rate, const double* doppler_bins, int nbins,
+                               prc_c64* out, int mem_kind, int device, void* stream, unsigned flags) {
+    if (!ref || !srv || !out) return fail(PRC_E_INVALID, "ref/srv/out must not be NULL");
+    if (mem_kind != PRC_MEM_DEVICE) return fail(PRC_E_INVALID, "prc_ls_multiple_frames_c64 takes device pointers (mem_kind=%d)", mem_kind);
+    if (n <= 0) return fail(PRC_E_INVALID, "n=%lld invalid", (long long)n);
+    if (nframes < 1 || nbins < 1) return fail(PRC_E_INVALID, "nframes=%d nbins=%d invalid", nframes, nbins);
+    if (nframes > 1 && frame_stride < n) return fail(PRC_E_INVALID, "frame_stride=%lld smaller than n=%lld", (long long)frame_stride, (long long)n);
+    Ctx* c;
+    TRY(get_ctx(device, stream, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    Batch bt;
+    bt.nf = nframes;
+    bt.stride = nframes > 1 ? frame_stride : n;
+    const size_t span = ((size_t)(nframes - 1) * bt.stride + n) * sizeof(float2);
+    const float2* dref = reinterpret_cast<const float2*>(ref);
+    const float2* cur = reinterpret_cast<const float2*>(srv);
+    float2* dout = reinterpret_cast<float2*>(out);
+    if (nbins > 1) TRY(c->clean.ensure(span));
+    if (nbins > 2) TRY(c->clean2.ensure(span));
+    // bins are applied one after the other on the running residual (clutter_removal.py:178-187); the last one
+    // writes the caller's buffer
+    for (int b = 0; b < nbins; ++b) {
+        const double fc = doppler_bins ? doppler_bins[b] : 0.0;
+        const bool last = (b == nbins - 1);
+        float2* dst = last ? dout : (((nbins - 1 - b) & 1) ? c->clean.as<float2>() : c->clean2.as<float2>());
+        TRY(ls_toeplitz_device(c, dref, cur, n, filter_len, peek, fc != 0.0, fc, sample_rate, dst, nullptr, bt));
+        if (!(flags & PRC_FLAG_ASYNC)) TRY(check_ls_status(c, 0, nframes));
+        cur = dst;
     }
     return finish(c, flags);
 }

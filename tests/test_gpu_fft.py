@@ -326,3 +326,38 @@ def test_nlms_large_batch_uses_the_half_size_ctas_and_matches():
         assert G.rel_inf(got[i], single, den=den) <= 2e-6
         assert G.rel_inf(gt[i], st1) <= 5e-5
     assert np.array_equal(got[0], got[4])          # same frame on another CTA: deterministic
+
+
+def test_ls_multiple_frames_batch_matches_single_calls_and_reference_golden():
+    """prc_ls_multiple_frames_c64 (what main.py:169-176 does per chunk, several chunks per call) against the drop-in
+    LS_Filter_Multiple frame by frame, and -- through it -- against the reference's own output (golden multi_main)."""
+    import torch
+    g = G.load("multi_main")
+    ref0, srv0 = G.inputs(g)
+    n, fl, fs, bins = ref0.shape[0], int(g["filter_len"]), float(g["sample_rate"]), [float(b) for b in g["bins"]]
+    others = [synth.make_frame(n, "P1", frame=90 + i) for i in range(2)]
+    frames = [(ref0, srv0)] + others
+    nf = len(frames)
+    dev = torch.device("cuda", 0)
+    stride = n + 32
+    ref_d = torch.zeros((nf, stride), dtype=torch.complex64, device=dev)
+    srv_d = torch.zeros((nf, stride), dtype=torch.complex64, device=dev)
+    for i, (r, s) in enumerate(frames):
+        ref_d[i, :n] = torch.from_numpy(r).to(dev)
+        srv_d[i, :n] = torch.from_numpy(s).to(dev)
+    out = torch.zeros((nf, stride), dtype=torch.complex64, device=dev)
+    lib = _lib.load()
+    st = torch.cuda.Stream(device=dev)
+    b64 = np.ascontiguousarray(bins, dtype=np.float64)
+    old = _lib.get_option("fft_min_n")
+    _lib.set_option("fft_min_n", 0)
+    try:
+        _lib.check(lib.prc_ls_multiple_frames_c64(ref_d.data_ptr(), srv_d.data_ptr(), n, nf, stride, fl, 10, fs, b64.ctypes.data, len(bins),
+                                                  out.data_ptr(), _lib.MEM_DEVICE, 0, st.cuda_stream, 0))
+        got = out.cpu().numpy()[:, :n]
+        for i, (r, s) in enumerate(frames):
+            want = prb.LS_Filter_Multiple(r, s, fl, fs, bins)
+            assert G.rel_inf(got[i], want, den=float(np.abs(s).max())) <= 2e-6, i
+    finally:
+        _lib.set_option("fft_min_n", old)
+    assert G.rel_inf(got[0][g["out_idx"]], g["out_sub"], den=float(g["srv_absmax"])) <= TOL
