@@ -361,3 +361,39 @@ def test_ls_multiple_frames_batch_matches_single_calls_and_reference_golden():
     finally:
         _lib.set_option("fft_min_n", old)
     assert G.rel_inf(got[0][g["out_idx"]], g["out_sub"], den=float(g["srv_absmax"])) <= TOL
+
+
+def test_random_shapes_fft_path_matches_direct_path_and_oracle():
+    """Randomised geometry check of the FFT-domain kernels (segment partition, circular wrap, N not a multiple of F, odd
+    decimation, short last segments): 16 seeded random shapes, FFT path against the direct-form path for every stage,
+    and against the CPU oracle for the CAF."""
+    from oracle import xambg_oracle as xo
+    rng = np.random.default_rng(20260924)
+    old = (_lib.get_option("fft"), _lib.get_option("fft_min_n"))
+    try:
+        for case in range(16):
+            n = int(rng.integers(4200, 90000))
+            F = int(rng.integers(2, max(3, min(200, n // 40))))
+            R = int(rng.integers(0, 260))
+            fl = int(rng.integers(1, 200))
+            peek = int(rng.integers(0, 12))
+            reg = float(rng.choice([0.5, 1.0, 3.0]))
+            use_win = bool(rng.integers(0, 2))
+            ref, srv = synth.make_frame(n, "P0" if case % 2 else "P1", frame=100 + case)
+            w = signal.get_window(("kaiser", 5.0), n) if use_win else None
+            res = {}
+            for mode in (1, 0):
+                _lib.set_option("fft", mode)
+                _lib.set_option("fft_min_n", 0)
+                cleaned, taps = prb.LS_Filter(ref, srv, fl, reg, peek, True)
+                amb = prb.fast_xambg(ref, srv, R, F, n, w)
+                res[mode] = (cleaned, taps, amb)
+            tag = (case, n, F, R, fl, peek)
+            assert G.rel_inf(res[1][1], res[0][1]) <= 3e-6, ("taps",) + tag
+            assert G.rel_inf(res[1][0], res[0][0], den=float(np.abs(srv).max())) <= 3e-6, ("cleaned",) + tag
+            assert G.rel_inf(res[1][2], res[0][2]) <= 3e-6, ("map",) + tag
+            if case % 4 == 0:
+                assert G.rel_inf(res[1][2], xo.fast_xambg_oracle(ref, srv, R, F, n, w)) <= TOL, ("oracle",) + tag
+    finally:
+        _lib.set_option("fft", old[0])
+        _lib.set_option("fft_min_n", old[1])
