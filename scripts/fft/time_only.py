@@ -20,7 +20,7 @@ if len(sys.argv) > 1:
     for kv in sys.argv[1:]:
         k, v = kv.split("=")
         _lib.set_option(k, int(v))
-for batch, slots in ((16, 3), (25, 3), (25, 2), (32, 2), (32, 3), (42, 3), (63, 2), (16, 4), (25, 5)):
+for batch, slots in ((25, 5),):
     pipe = FramePipeline(n, R, F, batch=batch, nslots=slots)
     for _ in range(3):
         pipe.run_device(ref_d, srv_d, maps)
