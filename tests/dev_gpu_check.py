@@ -1,5 +1,7 @@
-"""Development check of the FFT-domain path on a GPU box: errors against the float64 truths / the CPU oracle and a
-first timing.  Prints everything, asserts nothing (run under gpurun, read gpurun_out/fft_check.log)."""
+"""Development check of the FFT-domain path on a GPU box (not collected by pytest: no test_ prefix): errors against the
+float64 truths / the CPU oracle on both paths and a first timing.  Prints everything, asserts nothing.  It lives under
+tests/ because it uses the oracle, which only tests/, smoke() and bench.py's CPU arm may import.
+    python tests/dev_gpu_check.py"""
 import os
 import sys
 import time
@@ -7,7 +9,7 @@ import time
 import numpy as np
 import scipy.signal as signal
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import passiveradar_b200 as prb
 from passiveradar_b200 import _lib, synth
